@@ -1,0 +1,123 @@
+"""Host side of the fused decode: torch tensors in/out, libcnl_b200.so underneath.
+
+Mirrors the reference's decode interface (names, argument meaning, error behaviour):
+
+* ``decode_detections``       <- CenterNet.decode_detections        (reference models/centernet.py:229-241)
+* ``get_topk_from_heatmap``   <- CenterNet.get_topk_from_heatmap    (:243-261)
+* ``gather_and_decode_boxes`` <- CenterNet.gather_and_decode_boxes  (:263-304, staticmethod)
+* ``reid=`` argument          <- EmbeddingHead.gather_at_indices    (reference models/fairmot.py:63-73)
+
+torch is used for device memory and the current stream only; every arithmetic step runs in
+csrc/cnl_decode.cu.  There is no fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _ws(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _check_map(name: str, t: torch.Tensor, ndim: int = 4) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the cnl_b200 decode runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32 (got {t.dtype})")
+    if t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims (got shape {tuple(t.shape)})")
+    return t.contiguous()
+
+
+def decode_detections(heatmap: torch.Tensor, box_offsets: Optional[torch.Tensor], *, num_detections: int = 100,
+                      nms_kernel: int = 3, normalize_boxes: bool = False, box_log: bool = False,
+                      box_multiplier: float = 1.0, stride: int = 4, reid: Optional[torch.Tensor] = None,
+                      from_logits: bool = False, _force_generic: bool = False) -> Dict[str, torch.Tensor]:
+    """Returns {"boxes" (N,k,4) f32, "scores" (N,k) f32, "labels" (N,k) i64, "indices" (N,k) i64[, "embeddings" (N,k,E)]}.
+
+    ``heatmap`` holds probabilities (reference semantics) unless ``from_logits`` is set, in which case the
+    kernel applies the logistic itself (the fused form of ``outputs['heatmap'].sigmoid()``, reference :205)."""
+    lib = _lib.load()
+    heatmap = _check_map("heatmap", heatmap)
+    n, c, h, w = heatmap.shape
+    dev = heatmap.device
+    if box_offsets is not None:
+        box_offsets = _check_map("box_offsets", box_offsets)
+        if tuple(box_offsets.shape) != (n, 4, h, w):
+            raise ValueError(f"box_offsets must be {(n, 4, h, w)}, got {tuple(box_offsets.shape)}")
+    e = 0
+    if reid is not None:
+        reid = _check_map("reid", reid)
+        if reid.shape[0] != n or tuple(reid.shape[2:]) != (h, w):
+            raise ValueError(f"reid must be (N,E,{h},{w}), got {tuple(reid.shape)}")
+        e = reid.shape[1]
+    k = int(num_detections)
+    with torch.cuda.device(dev):
+        scores = torch.empty((n, k), dtype=torch.float32, device=dev)
+        labels = torch.empty((n, k), dtype=torch.int64, device=dev)
+        indices = torch.empty((n, k), dtype=torch.int64, device=dev)
+        boxes = torch.empty((n, k, 4), dtype=torch.float32, device=dev) if box_offsets is not None else None
+        emb = torch.empty((n, k, e), dtype=torch.float32, device=dev) if reid is not None else None
+        nbytes = lib.cnl_decode_workspace_bytes(n, h, w)
+        ws = _ws(dev, nbytes)
+        st = lib.cnl_decode_detections(
+            heatmap.data_ptr(), box_offsets.data_ptr() if box_offsets is not None else None,
+            reid.data_ptr() if reid is not None else None,
+            n, c, h, w, e, int(bool(from_logits)), -int(nms_kernel) if _force_generic else int(nms_kernel), k,
+            int(bool(normalize_boxes)), int(bool(box_log)), float(box_multiplier), int(stride),
+            boxes.data_ptr() if boxes is not None else None, scores.data_ptr(), labels.data_ptr(), indices.data_ptr(),
+            emb.data_ptr() if emb is not None else None,
+            ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "cnl_decode_detections")
+    out = {"scores": scores, "labels": labels, "indices": indices}
+    if boxes is not None:
+        out["boxes"] = boxes
+    if emb is not None:
+        out["embeddings"] = emb
+    return out
+
+
+def get_topk_from_heatmap(heatmap: torch.Tensor, num_detections: int = 100, nms_kernel: int = 3,
+                          pseudo_nms: bool = True, from_logits: bool = False):
+    """(scores, indices, labels), each (N,k) - reference models/centernet.py:243-261."""
+    out = decode_detections(heatmap, None, num_detections=num_detections,
+                            nms_kernel=nms_kernel if pseudo_nms else 1, from_logits=from_logits)
+    return out["scores"], out["indices"], out["labels"]
+
+
+def gather_and_decode_boxes(box_offsets: torch.Tensor, indices: torch.Tensor, normalize_boxes: bool = False,
+                            box_log: bool = False, box_multiplier: float = 1.0, stride: int = 4) -> torch.Tensor:
+    """reference models/centernet.py:263-304.  Batch dim optional, as in the reference ((4,H,W) + (k,))."""
+    lib = _lib.load()
+    squeeze = box_offsets.dim() == 3
+    if squeeze:
+        box_offsets, indices = box_offsets.unsqueeze(0), indices.unsqueeze(0)
+    box_offsets = _check_map("box_offsets", box_offsets)
+    n, four, h, w = box_offsets.shape
+    if four != 4:
+        raise ValueError("box_offsets must have 4 channels (left, top, right, bottom)")
+    if indices.dtype != torch.int64 or indices.dim() != 2 or indices.shape[0] != n or not indices.is_cuda:
+        raise ValueError("indices must be a CUDA int64 tensor of shape (N, k)")
+    indices = indices.contiguous()
+    k = indices.shape[1]
+    dev = box_offsets.device
+    with torch.cuda.device(dev):
+        boxes = torch.empty((n, k, 4), dtype=torch.float32, device=dev)
+        st = lib.cnl_gather_boxes(box_offsets.data_ptr(), indices.data_ptr(), n, h, w, k, int(bool(normalize_boxes)),
+                                  int(bool(box_log)), float(box_multiplier), int(stride), boxes.data_ptr(),
+                                  torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "cnl_gather_boxes")
+    return boxes[0] if squeeze else boxes

@@ -1,0 +1,8 @@
+"""Importable alias for the package directory ``centernet-lightning_b200/`` (the hyphen in the
+directory name, fixed by the repo layout, is not a valid Python identifier)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "centernet-lightning_b200")
+__path__.insert(0, _real)
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

@@ -1,0 +1,145 @@
+/* cnl_b200.h - C ABI of the sm_100a CenterNet inference hot path.
+ *
+ * The reference (gau-nernst/centernet-lightning) has no FFI/plugin registry: its hot path
+ * is a Python object boundary.  Each entry point below names the reference
+ * function it replaces (paths relative to the reference root).  All pointers are raw
+ * DEVICE pointers unless the name ends in _host; all calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*), never synchronise, never allocate tensor memory
+ * (the caller owns outputs and workspace) and return 0 on success or a cnl_status.
+ * The reference-side binding is the ctypes stub shown in INTEGRATION.md.
+ */
+#ifndef CNL_B200_H_
+#define CNL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef enum {
+  CNL_OK = 0,
+  CNL_ERR_INVALID_ARGUMENT = 1,   /* shapes / k > H*W / even nms kernel / misaligned pointer */
+  CNL_ERR_UNSUPPORTED = 2,        /* configuration the sm_100a kernels do not implement       */
+  CNL_ERR_CUDA = 3,               /* a CUDA runtime / driver call failed                      */
+  CNL_ERR_WORKSPACE = 4           /* workspace too small                                      */
+} cnl_status;
+
+/* Human-readable description of the last error on the calling thread. */
+const char* cnl_last_error(void);
+
+/* Library/ABI version (major*1000 + minor) and the SM architecture it was compiled for (100). */
+int cnl_version(void);
+int cnl_compiled_sm(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Decode: heatmap -> top-k detections.
+ *
+ * Replaces CenterNet.decode_detections / get_topk_from_heatmap / gather_and_decode_boxes
+ * (centernet_lightning/models/centernet.py:229-304) and, when `reid` is non-NULL,
+ * EmbeddingHead.gather_at_indices / FairMOT.gather_tracking2d
+ * (centernet_lightning/models/fairmot.py:63-73, 138-151).
+ *
+ *   heatmap      (N, C, H, W) float32, contiguous NCHW.
+ *                from_logits = 0: probabilities, exactly what the reference's decode receives
+ *                                 (validation_step applies .sigmoid() first, centernet.py:205).
+ *                from_logits = 1: raw head output; the kernel applies 1/(1+exp(-x)) in fp32 itself
+ *                                 (fuses the sigmoid of centernet.py:205 into the same pass).
+ *   box_offsets  (N, 4, H, W) float32 ltrb map, or NULL together with boxes (top-k only).
+ *   reid         (N, E, H, W) float32 or NULL (E = reid_dim).
+ *   nms_kernel   odd, 1..7 (centernet.py:93 default 3).  k = num_detections <= min(H*W, 1024).
+ *   Outputs (caller-allocated): boxes (N,k,4) f32 xyxy; scores (N,k) f32 descending;
+ *   labels (N,k) int64; indices (N,k) int64 flat y*W+x; embeddings (N,k,E) f32 or NULL.
+ *   Tie order: score descending, then flat index ascending (torch.topk leaves it unspecified).
+ *   workspace: cnl_decode_workspace_bytes(N,H,W) bytes, 256-byte aligned; contents are scratch.
+ * ------------------------------------------------------------------------------------------ */
+size_t cnl_decode_workspace_bytes(int n, int h, int w);
+
+int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
+                          int n, int c, int h, int w, int reid_dim,
+                          int from_logits, int nms_kernel, int num_detections,
+                          int normalize_boxes, int box_log, float box_multiplier, int stride,
+                          float* boxes, float* scores, int64_t* labels, int64_t* indices,
+                          float* embeddings,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone box gather for caller-supplied indices: CenterNet.gather_and_decode_boxes
+ * (centernet_lightning/models/centernet.py:263-304, a staticmethod the reference also calls from its
+ * loss, :162-165).  indices (N,k) int64 device; boxes (N,k,4) f32, 16-byte aligned.  Out-of-range
+ * indices (torch.gather would raise) produce NaN rows. */
+int cnl_gather_boxes(const float* box_offsets, const int64_t* indices, int n, int h, int w, int k,
+                     int normalize_boxes, int box_log, float box_multiplier, int stride,
+                     float* boxes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Forward: backbone -> neck -> heads as a list of fused convolution launches.
+ *
+ * Replaces GenericModel.forward (centernet_lightning/models/meta.py:41-47) and the
+ * vision_toolbox backbone/neck/ConvBnAct modules it calls (meta.py:9-10, 21-30, 87-96).
+ * A cnl_engine is an immutable plan for one (batch, height, width): packed fp16 weights,
+ * TMA descriptors and activation buffer offsets.  The caller provides one arena of
+ * cnl_engine_arena_bytes() bytes of device memory; the engine never allocates tensors.
+ *
+ * precision: 0 = CNL_PRECISION_SPLIT  activations and weights are carried as fp16 hi+lo pairs and
+ *                every product is accumulated in fp32 from three tcgen05 passes (hi*hi, hi*lo, lo*hi):
+ *                fp32-equivalent results (the 1e-3 parity bar of BASELINE.json).
+ *            1 = CNL_PRECISION_FAST   single fp16 pass, fp32 accumulate (reduced precision, reported
+ *                separately; does not meet the 1e-3 bar).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cnl_engine cnl_engine;
+
+enum { CNL_PRECISION_SPLIT = 0, CNL_PRECISION_FAST = 1 };
+
+/* One fused convolution: out = act(conv(in, w) + bias [+ residual]).  Host-side description. */
+typedef struct {
+  int kind;            /* 0 = conv (tcgen05 implicit GEMM), 1 = stem (7x7/2 conv + ReLU + 3x3/2 max-pool) */
+  int src, dst;        /* buffer ids                                                                      */
+  int cin, cout;       /* real channel counts                                                             */
+  int ksize, stride, pad;
+  int relu;
+  int src_c_off, dst_c_off;
+  int residual;        /* buffer id or -1                                                                 */
+  int residual_up;     /* 1 or 2 (nearest-upsampled half-resolution residual)                             */
+  const float* weight_host;   /* (cout, cin, k, k) fp32, BatchNorm already folded                         */
+  const float* bias_host;     /* (cout,) fp32                                                             */
+} cnl_conv_desc;
+
+typedef struct {
+  int channels;
+  int stride;          /* spatial size = (height/stride, width/stride)            */
+  int fp32_nchw;       /* 1: (N,C,H,W) float32 (image input, head outputs)        */
+} cnl_buffer_desc;
+
+int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_buffers,
+                      const cnl_conv_desc* ops, int n_ops,
+                      int batch, int height, int width, int precision, int device);
+void cnl_engine_destroy(cnl_engine* e);
+
+/* Bytes of device memory the engine needs for weights + activations, and the byte offset of a
+ * buffer inside the arena (head outputs are read by the caller from there). */
+size_t cnl_engine_arena_bytes(const cnl_engine* e);
+size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer);
+
+/* Upload packed weights into the arena (once, or again after a weight change). */
+int cnl_engine_upload(cnl_engine* e, void* arena, void* stream);
+
+/* Run ops [first_op, last_op) on `stream`.  image: (N,3,H,W) fp32 device pointer (buffer 0 is bound
+ * to it).  CUDA-graph capturable.  Returns the number of kernels launched in *launches if non-NULL. */
+int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first_op, int last_op,
+                       void* stream, int* launches);
+
+/* Debug / test helpers: convert an NHWC-fp16(hi[,lo]) activation buffer to (N,C,H,W) fp32 and back. */
+int cnl_engine_read_buffer(cnl_engine* e, void* arena, int buffer, float* out_nchw, void* stream);
+int cnl_engine_write_buffer(cnl_engine* e, void* arena, int buffer, const float* in_nchw, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNL_B200_H_ */

@@ -1,0 +1,73 @@
+"""Seeded input recipes shared by the golden generator and the tests (inputs are regenerated, never stored)."""
+from __future__ import annotations
+
+import torch
+
+
+def _c(name, n, c, h, w, k=100, nms=3, seed=0, logits=True, normalize=False, box_log=False, mult=16.0, stride=4,
+       reid=0, kind="randn"):
+    return dict(name=name, n=n, c=c, h=h, w=w, k=k, nms=nms, seed=seed, logits=logits, normalize=normalize,
+                box_log=box_log, mult=mult, stride=stride, reid=reid, kind=kind)
+
+
+# SURVEY 8c "golden vectors to create": seeds x shapes x k x nms_kernel x box_log x normalize + adversarial maps.
+DECODE_CASES = [
+    _c("coco128_s0", 2, 80, 128, 128, seed=0),
+    _c("coco128_s1", 2, 80, 128, 128, seed=1),
+    _c("coco128_s2_k300", 1, 80, 128, 128, seed=2, k=300),
+    _c("track128", 1, 2, 128, 128, seed=0, reid=64),
+    _c("big256", 1, 80, 256, 256, seed=0),
+    _c("odd17x23", 3, 5, 17, 23, seed=0, k=50),
+    _c("odd17x23_k1", 3, 5, 17, 23, seed=1, k=1),
+    _c("nms1", 2, 7, 32, 64, seed=0, nms=1, k=64),
+    _c("nms5", 2, 7, 32, 64, seed=1, nms=5, k=20),
+    _c("nms5_odd", 2, 3, 19, 21, seed=2, nms=5, k=9),
+    _c("nms7_odd", 1, 3, 19, 21, seed=3, nms=7, k=4),
+    _c("boxlog", 2, 80, 64, 64, seed=0, box_log=True, mult=1.0),
+    _c("normalize", 2, 80, 64, 64, seed=1, normalize=True),
+    _c("wide272", 1, 4, 8, 272, seed=0, k=30),
+    _c("k_eq_hw", 1, 3, 6, 8, seed=0, k=48),
+    _c("plateau", 1, 3, 16, 16, seed=0, k=10, kind="plateau"),
+    _c("saturated", 1, 4, 16, 16, seed=0, k=10, kind="saturated"),
+    _c("corners", 1, 2, 16, 32, seed=0, k=8, kind="corners"),
+    _c("probs_direct", 2, 6, 32, 32, seed=4, k=40, logits=False),
+]
+DECODE_BY_NAME = {c["name"]: c for c in DECODE_CASES}
+
+
+def make_decode_inputs(case):
+    """(heat, box, reid).  heat = logits when case['logits'] else probabilities in (0,1)."""
+    g = torch.Generator().manual_seed(case["seed"])
+    n, c, h, w = case["n"], case["c"], case["h"], case["w"]
+    kind = case["kind"]
+    if kind == "randn":
+        heat = torch.randn((n, c, h, w), generator=g) * 1.5 - 2.19          # SURVEY 8d decode-only benchmark recipe
+    elif kind == "plateau":                                                   # every pixel equal: all are "peaks"
+        heat = torch.full((n, c, h, w), -1.0)
+        heat[:, 1, 4:9, 4:9] = 0.5                                            # a flat 5x5 mesa in class 1
+    elif kind == "saturated":                                                 # |logit| > 20: sigmoid collapses to 0 / 1
+        heat = torch.randn((n, c, h, w), generator=g) * 30.0
+    elif kind == "corners":                                                   # one peak in every corner / border
+        heat = torch.full((n, c, h, w), -8.0)
+        for i, (y, x) in enumerate([(0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1), (0, w // 2), (h // 2, 0)]):
+            heat[:, i % c, y, x] = 1.0 + 0.25 * i
+    else:
+        raise ValueError(kind)
+    if not case["logits"]:
+        heat = torch.rand((n, c, h, w), generator=g)
+    box = torch.randn((n, 4, h, w), generator=g)
+    if case["box_log"]:
+        box = box * 0.5
+    reid = torch.randn((n, case["reid"], h, w), generator=g) if case["reid"] else None
+    return heat, box, reid
+
+
+FORWARD_CASES = {
+    "det64": dict(model=dict(num_classes=80), seed=0, n=2, size=64, img_seed=7),
+    "track64": dict(model=dict(num_classes=2, reid_dim=64), seed=1, n=1, size=64, img_seed=8),
+}
+
+
+def make_image(kw):
+    g = torch.Generator().manual_seed(kw["img_seed"])
+    return torch.rand((kw["n"], 3, kw["size"], kw["size"]), generator=g)
