@@ -1,13 +1,798 @@
-// placeholder until the tcgen05 engine lands (next commit)
+// sm_100a forward engine: backbone -> neck -> heads as a list of fused implicit-GEMM convolutions.
+//
+// Replaces GenericModel.forward (reference centernet_lightning/models/meta.py:41-47) and the vision_toolbox
+// backbone / FPN / ConvBnAct modules it calls (meta.py:9-10, 21-30, 87-96).
+//
+// Data layout in HBM
+//   activations : NHWC, fp16.  CNL_PRECISION_SPLIT keeps two planes per tensor, [plane][N][H][W][C]:
+//                 plane 0 = hi = fp16(x), plane 1 = lo = fp16(x - hi); x ~ hi + lo carries ~22 mantissa bits.
+//   weights     : [plane][tap][Cout_pad][Cin] fp16 (K-major rows for the UMMA B operand), BatchNorm folded,
+//                 scaled by a per-op power of two so that the lo parts stay in fp16's normal range.
+//   head outputs: (N,C,H,W) fp32, the layout the decode kernel and the reference API use.
+//
+// conv_tc_kernel (one launch per ConvOp, persistent, 1 CTA/SM, 192 threads)
+//   GEMM view: M = 128 output pixels (a th x tw patch of one image), N = Cout tile (<= 256), K = taps x Cin.
+//   warp 0    : TMA producer.  For every (tap, 64-channel block) one 4-D tiled TMA load brings the shifted input
+//               patch [th][tw][64ch] straight into the 128B-swizzled K-major A tile (out-of-bounds rows/columns are
+//               zero-filled by the TMA unit = conv padding; stride-2 convs use the tensor map's element strides),
+//               and one 3-D load brings the [Cout_tile][64] weight tile.  mbarrier ring of `num_stages` stages.
+//   warp 1    : allocates 512 TMEM columns (2 x 256-column fp32 accumulators) and issues tcgen05.mma
+//               (cta_group::1, kind::f16, M=128, N=Cout_tile, K=16).  SPLIT precision issues hi*hi, hi*lo, lo*hi
+//               into the same accumulator.  tcgen05.commit frees smem stages and publishes finished accumulators.
+//   warps 2-5 : epilogue.  tcgen05.ld the accumulator (one pixel row per thread), scale + bias (+ residual,
+//               optionally nearest-upsampled for the FPN top-down add) + ReLU, split into hi/lo fp16, stage in
+//               128B-swizzled smem and TMA-store NHWC; head outputs are written directly as fp32 NCHW.
+//               The double-buffered accumulator lets the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
 #include "cnl_common.h"
-using namespace cnl;
-extern "C" {
-int cnl_engine_create(cnl_engine**, const cnl_buffer_desc*, int, const cnl_conv_desc*, int, int, int, int, int, int) { return fail(CNL_ERR_UNSUPPORTED, "engine not built"); }
-void cnl_engine_destroy(cnl_engine*) {}
-size_t cnl_engine_arena_bytes(const cnl_engine*) { return 0; }
-size_t cnl_engine_buffer_offset(const cnl_engine*, int) { return 0; }
-int cnl_engine_upload(cnl_engine*, void*, void*) { return fail(CNL_ERR_UNSUPPORTED, "engine not built"); }
-int cnl_engine_forward(cnl_engine*, void*, const float*, int, int, void*, int*) { return fail(CNL_ERR_UNSUPPORTED, "engine not built"); }
-int cnl_engine_read_buffer(cnl_engine*, void*, int, float*, void*) { return fail(CNL_ERR_UNSUPPORTED, "engine not built"); }
-int cnl_engine_write_buffer(cnl_engine*, void*, int, const float*, void*) { return fail(CNL_ERR_UNSUPPORTED, "engine not built"); }
+#include "cnl_tcgen05.cuh"
+
+namespace cnl {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                  // 64 fp16 = one 128-byte swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 192;
+constexpr int kSmemLimit = 232448 - 1024;    // 227 KB opt-in shared memory per CTA minus the static part (barriers)
+constexpr int kStageWarpBytes = 32 * 128;    // epilogue staging: 32 pixels x 64 channels fp16 per warp and plane
+
+struct ConvParams {
+  int n_img, out_h, out_w;
+  int tw, th, tiles_w, tiles_h, m_tiles;
+  int n_tiles, n_tile;
+  int ksize, stride, pad, kblocks;
+  int src_c_off, dst_c_off;
+  int relu;
+  int out_mode;                 // 0 = NHWC fp16 planes via TMA store, 1 = NCHW fp32 direct stores
+  int cout_real;
+  float wscale_inv;
+  const float* bias;            // [n_tiles * n_tile]
+  float* out_nchw;
+  const __half* res;            // residual NHWC planes (or nullptr)
+  int res_up, res_c, res_h, res_w;
+  long long res_plane_elems;
+  int num_stages;
+  int store_w, store_h;         // per-warp TMA store box in pixels (store_w * store_h == 32)
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// The implicit-GEMM convolution kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int NPLANE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap w_map,
+               const __grid_constant__ CUtensorMap dst_map, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+  const int b_tile_bytes = p.n_tile * kBlockK * 2;
+  const int stage_bytes = NPLANE * (kATileBytes + b_tile_bytes);
+  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;        // [4 warps][NPLANE][4096], 1024-aligned
+  const int taps = p.ksize * p.ksize;
+  const int k_iters = taps * p.kblocks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&src_map);
+    ptx::prefetch_tmap(&w_map);
+    if (p.out_mode == 0) ptx::prefetch_tmap(&dst_map);
+    for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_base_smem, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ==============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.n_tiles;
+        int m_idx = tile / p.n_tiles;
+        const int img = m_idx / (p.tiles_h * p.tiles_w);
+        m_idx -= img * (p.tiles_h * p.tiles_w);
+        const int h0 = (m_idx / p.tiles_w) * p.th;
+        const int w0 = (m_idx % p.tiles_w) * p.tw;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.ksize, s = tap - r * p.ksize;
+          const int cw = w0 * p.stride + s - p.pad;
+          const int ch = h0 * p.stride + r - p.pad;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            uint8_t* st = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl)
+              ptx::tma_load_4d(st + pl * kATileBytes, &src_map, &full_bar[stage], p.src_c_off + kb * kBlockK, cw, ch,
+                               img + pl * p.n_img);
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl)
+              ptx::tma_load_3d(st + NPLANE * kATileBytes + pl * b_tile_bytes, &w_map, &full_bar[stage], kb * kBlockK,
+                               n_idx * p.n_tile, tap + pl * taps);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =================================================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+        const int as = acc_it & 1;
+        const uint32_t aphase = (acc_it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int it = 0; it < k_iters; ++it) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + NPLANE * kATileBytes;
+          const uint64_t a_hi = ptx::make_sw128_kmajor_desc(a_addr);
+          const uint64_t b_hi = ptx::make_sw128_kmajor_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);        // +32 bytes along K inside the swizzled row
+            ptx::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, (it | k) != 0);
+            if (NPLANE == 2) {
+              const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + kATileBytes);
+              const uint64_t b_lo = ptx::make_sw128_kmajor_desc(b_addr + b_tile_bytes);
+              ptx::umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+              ptx::umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);          // smem stage reusable once these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full_bar[as]);           // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================================== epilogue (warps 2..5) =====================================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int lane_base = q * 32;
+    uint8_t* my_stage = staging + (size_t)(warp - 2) * NPLANE * kStageWarpBytes;
+    int acc_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+      const int as = acc_it & 1;
+      const uint32_t aphase = (acc_it >> 1) & 1;
+      const int n_idx = tile % p.n_tiles;
+      int m_idx = tile / p.n_tiles;
+      const int img = m_idx / (p.tiles_h * p.tiles_w);
+      m_idx -= img * (p.tiles_h * p.tiles_w);
+      const int h0 = (m_idx / p.tiles_w) * p.th;
+      const int w0 = (m_idx % p.tiles_w) * p.tw;
+      const int pix = lane_base + lane;
+      const int h = h0 + pix / p.tw, w = w0 + pix % p.tw;
+      const bool valid = (h < p.out_h) && (w < p.out_w);
+
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + as * 256;
+
+      if (p.out_mode == 0) {
+        const __half* res_px = nullptr;
+        if (p.res != nullptr && valid)
+          res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
+        for (int c64 = 0; c64 < p.n_tile / 64; ++c64) {
+          uint32_t r[64];
+          ptx::tmem_ld_32x32b_x32(taddr + c64 * 64, r);
+          ptx::tmem_ld_32x32b_x32(taddr + c64 * 64 + 32, r + 32);
+          ptx::tmem_ld_wait();
+          const int cb = n_idx * p.n_tile + c64 * 64;
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+            v[j + 0] = fmaf(__uint_as_float(r[j + 0]), p.wscale_inv, b4.x);
+            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), p.wscale_inv, b4.y);
+            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), p.wscale_inv, b4.z);
+            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), p.wscale_inv, b4.w);
+          }
+          if (res_px != nullptr) {
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res_px + pl * p.res_plane_elems + cb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 u = __ldg(rp + j);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(h2[t]);
+                  v[j * 8 + 2 * t] += f.x;
+                  v[j * 8 + 2 * t + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          // previous TMA store out of this warp's staging buffers must have finished reading them
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                  // 8 channels = one 16-byte chunk, XOR-swizzled by row
+            uint4 hi, lo;
+            __half2* hh = reinterpret_cast<__half2*>(&hi);
+            __half2* ll = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float a = v[j * 8 + 2 * t], b = v[j * 8 + 2 * t + 1];
+              const __half2 h2 = __floats2half2_rn(a, b);
+              hh[t] = h2;
+              if (NPLANE == 2) {
+                const float2 back = __half22float2(h2);
+                ll[t] = __floats2half2_rn(a - back.x, b - back.y);
+              }
+            }
+            const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
+            *reinterpret_cast<uint4*>(my_stage + off) = hi;
+            if (NPLANE == 2) *reinterpret_cast<uint4*>(my_stage + kStageWarpBytes + off) = lo;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl)
+              ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + cb, wq, hq, img + pl * p.n_img);
+            ptx::tma_store_commit();
+          }
+        }
+      } else {
+        for (int c16 = 0; c16 < p.n_tile / 16; ++c16) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c16 * 16, r);
+          ptx::tmem_ld_wait();
+          const int cb = n_idx * p.n_tile + c16 * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = cb + j;
+            if (valid && c < p.cout_real) {
+              float val = fmaf(__uint_as_float(r[j]), p.wscale_inv, __ldg(p.bias + c));
+              if (p.relu) val = fmaxf(val, 0.0f);
+              p.out_nchw[(((long long)img * p.cout_real + c) * p.out_h + h) * p.out_w + w] = val;
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+    }
+    if (lane == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Stem: conv7x7/2 (3->64) + bias + ReLU on CUDA cores (Cin = 3 has no tensor-core shape), then 3x3/2 max-pool.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kStemTile = 16;                                  // 16x16 conv outputs per CTA
+constexpr int kStemPatch = kStemTile * 2 + 5;                  // 37 input rows/cols
+constexpr int kStemSmemBytes = (3 * kStemPatch * kStemPatch + 147 * 64) * 4;
+
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ image, const float* __restrict__ wk /*[147][64]*/, const float* __restrict__ bias,
+                 float* __restrict__ out /*[N][H/2][W/2][64] fp32*/, int H, int W) {
+  extern __shared__ float s_mem[];
+  float* s_in = s_mem;                                         // [3][37][37]
+  float* s_w = s_mem + 3 * kStemPatch * kStemPatch;            // [147][64]
+  const int OH = H / 2, OW = W / 2;
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < 147 * 64; i += 256) s_w[i] = wk[i];
+  for (int i = threadIdx.x; i < 3 * kStemPatch * kStemPatch; i += 256) {
+    int c = i / (kStemPatch * kStemPatch);
+    int rem = i - c * kStemPatch * kStemPatch;
+    int y = iy0 + rem / kStemPatch, x = ix0 + rem % kStemPatch;
+    s_in[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(image + (((size_t)n * 3 + c) * H + y) * W + x) : 0.0f;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 7; ++r) {
+      const float* in_row = s_in + (c * kStemPatch + 2 * ty + r) * kStemPatch + 2 * tx;
+      const float* w_row = s_w + ((c * 7 + r) * 7) * 64;
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float x = in_row[s];
+        const float4* w4 = reinterpret_cast<const float4*>(w_row + s * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 wv = w4[j];
+          acc[4 * j + 0] = fmaf(x, wv.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(x, wv.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(x, wv.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(x, wv.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < OH && ox < OW) {
+    float4* o4 = reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox) * 64);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j);
+      o4[j] = make_float4(fmaxf(acc[4 * j] + b.x, 0.f), fmaxf(acc[4 * j + 1] + b.y, 0.f), fmaxf(acc[4 * j + 2] + b.z, 0.f),
+                          fmaxf(acc[4 * j + 3] + b.w, 0.f));
+    }
+  }
+}
+
+// 3x3 stride-2 pad-1 max-pool over the fp32 NHWC stem output -> NHWC fp16 planes.  One thread = one pixel x 8 channels.
+template <int NPLANE>
+__global__ void stem_pool_kernel(const float* __restrict__ in /*[N][IH][IW][64]*/, __half* __restrict__ out, int N, int IH,
+                                 int IW, long long plane_elems) {
+  const int OH = IH / 2, OW = IW / 2;
+  const long long total = (long long)N * OH * OW * 8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c8 = (int)(t & 7);
+  long long pix = t >> 3;
+  const int ox = (int)(pix % OW);
+  pix /= OW;
+  const int oy = (int)(pix % OH);
+  const int n = (int)(pix / OH);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y = 2 * oy + dy;
+    if (y < 0 || y >= IH) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = 2 * ox + dx;
+      if (x < 0 || x >= IW) continue;
+      const float4* p4 = reinterpret_cast<const float4*>(in + (((size_t)n * IH + y) * IW + x) * 64 + c8 * 8);
+      const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+      m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+    }
+  }
+  uint4 hi, lo;
+  __half2* hh = reinterpret_cast<__half2*>(&hi);
+  __half2* ll = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 h2 = __floats2half2_rn(m[2 * j], m[2 * j + 1]);
+    hh[j] = h2;
+    const float2 back = __half22float2(h2);
+    ll[j] = __floats2half2_rn(m[2 * j] - back.x, m[2 * j + 1] - back.y);
+  }
+  const size_t o = (((size_t)n * OH + oy) * OW + ox) * 64 + c8 * 8;
+  *reinterpret_cast<uint4*>(out + o) = hi;
+  if (NPLANE == 2) *reinterpret_cast<uint4*>(out + plane_elems + o) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Layout converters (tests / debugging): NHWC fp16 planes <-> NCHW fp32
+// ------------------------------------------------------------------------------------------------------------
+__global__ void planes_to_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W,
+                                      int planes, long long plane_elems) {
+  const long long total = (long long)N * C * H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  long long rest = t / C;
+  const int w = (int)(rest % W); rest /= W;
+  const int h = (int)(rest % H);
+  const int n = (int)(rest / H);
+  float v = __half2float(in[t]);
+  if (planes == 2) v += __half2float(in[plane_elems + t]);
+  out[(((long long)n * C + c) * H + h) * W + w] = v;
+}
+__global__ void nchw_to_planes_kernel(const float* __restrict__ in, __half* __restrict__ out, int N, int C, int H, int W,
+                                      int planes, long long plane_elems) {
+  const long long total = (long long)N * C * H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  long long rest = t / C;
+  const int w = (int)(rest % W); rest /= W;
+  const int h = (int)(rest % H);
+  const int n = (int)(rest / H);
+  const float v = in[(((long long)n * C + c) * H + h) * W + w];
+  const __half hi = __float2half_rn(v);
+  out[t] = hi;
+  if (planes == 2) out[plane_elems + t] = __float2half_rn(v - __half2float(hi));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host: engine
+// ------------------------------------------------------------------------------------------------------------
+struct BufferInfo {
+  int channels, stride, fp32_nchw;
+  int h, w;
+  size_t offset, bytes;
+  long long plane_elems;
+};
+
+struct OpInfo {
+  cnl_conv_desc d;
+  // conv
+  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h;
+  float wscale;
+  size_t w_offset, bias_offset, scratch_offset;
+  std::vector<__half> w_packed;       // [plane][tap][cout_pad][cin]
+  std::vector<float> bias_packed;     // [cout_pad]   (stem: [64]);
+  std::vector<float> w_stem;          // stem: [147][64] fp32
+  CUtensorMap src_map, w_map, dst_map;
+};
+
+}  // namespace cnl
+
+struct cnl_engine {
+  int batch, height, width, precision, planes, device, num_sms;
+  std::vector<cnl::BufferInfo> bufs;
+  std::vector<cnl::OpInfo> ops;
+  size_t arena_bytes;
+  void* uploaded_arena;
+};
+
+namespace cnl {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const cuuint32_t* estride, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(CNL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides_bytes, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CNL_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return CNL_OK;
+}
+
+static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+static void split_half(float x, __half* hi, __half* lo) {
+  *hi = __float2half_rn(x);
+  *lo = __float2half_rn(x - __half2float(*hi));
+}
+
+static int prepare_conv(cnl_engine* e, OpInfo& op) {
+  const cnl_conv_desc& d = op.d;
+  const BufferInfo& src = e->bufs[d.src];
+  const BufferInfo& dst = e->bufs[d.dst];
+  if (src.fp32_nchw) return fail(CNL_ERR_UNSUPPORTED, "conv input must be an NHWC fp16 buffer");
+  if (d.cin % 64 || d.src_c_off % 64) return fail(CNL_ERR_UNSUPPORTED, "conv Cin/src_c_off must be multiples of 64 (got %d/%d)", d.cin, d.src_c_off);
+  if (d.src_c_off + d.cin > src.channels) return fail(CNL_ERR_INVALID_ARGUMENT, "conv reads past the source channels");
+  if (d.ksize != 1 && d.ksize != 3) return fail(CNL_ERR_UNSUPPORTED, "conv kernel size %d (1 and 3 are implemented)", d.ksize);
+  if (d.stride != 1 && d.stride != 2) return fail(CNL_ERR_UNSUPPORTED, "conv stride %d", d.stride);
+  if (src.h / d.stride != dst.h || src.w / d.stride != dst.w) return fail(CNL_ERR_INVALID_ARGUMENT, "conv output size mismatch");
+  if (d.cout % 256 == 0) { op.n_tile = 256; op.cout_pad = d.cout; }
+  else if (d.cout <= 256) { op.cout_pad = (d.cout + 15) / 16 * 16; op.n_tile = op.cout_pad; }
+  else return fail(CNL_ERR_UNSUPPORTED, "conv Cout=%d (must be <= 256 or a multiple of 256)", d.cout);
+  op.n_tiles = op.cout_pad / op.n_tile;
+  if (!dst.fp32_nchw) {
+    if (d.cout % 64 || d.dst_c_off % 64) return fail(CNL_ERR_UNSUPPORTED, "NHWC conv output needs Cout %% 64 == 0");
+    if (d.dst_c_off + d.cout > dst.channels) return fail(CNL_ERR_INVALID_ARGUMENT, "conv writes past the destination channels");
+  } else if (d.cout != dst.channels || d.dst_c_off != 0) {
+    return fail(CNL_ERR_INVALID_ARGUMENT, "fp32 NCHW output must cover the whole buffer");
+  }
+  if (d.residual >= 0) {
+    const BufferInfo& rb = e->bufs[d.residual];
+    if (rb.fp32_nchw || dst.fp32_nchw) return fail(CNL_ERR_UNSUPPORTED, "residual needs NHWC buffers");
+    if (rb.channels != d.cout || rb.h * d.residual_up != dst.h || rb.w * d.residual_up != dst.w)
+      return fail(CNL_ERR_INVALID_ARGUMENT, "residual shape mismatch");
+  }
+  op.tw = std::max(8, std::min(128, pow2_ceil(dst.w)));
+  op.th = kBlockM / op.tw;
+  op.tiles_w = (dst.w + op.tw - 1) / op.tw;
+  op.tiles_h = (dst.h + op.th - 1) / op.th;
+  op.store_w = std::min(op.tw, 32);
+  op.store_h = 32 / op.store_w;
+  const int planes = e->planes;
+  const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
+  const int staging = dst.fp32_nchw ? 0 : 4 * planes * kStageWarpBytes;
+  op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / stage_bytes);
+  if (op.num_stages < 2) return fail(CNL_ERR_UNSUPPORTED, "conv tile does not fit shared memory");
+
+  // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
+  const int taps = d.ksize * d.ksize;
+  float wmax = 0.f;
+  const size_t nw = (size_t)d.cout * d.cin * taps;
+  for (size_t i = 0; i < nw; ++i) wmax = std::max(wmax, std::fabs(d.weight_host[i]));
+  int ex = 0;
+  if (wmax > 0.f) { std::frexp(wmax, &ex); }
+  op.wscale = std::ldexp(1.0f, 13 - ex);               // max |w| * wscale in [4096, 8192)
+  op.w_packed.assign((size_t)planes * taps * op.cout_pad * d.cin, __float2half_rn(0.f));
+  for (int co = 0; co < d.cout; ++co)
+    for (int ci = 0; ci < d.cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const float w = d.weight_host[((size_t)co * d.cin + ci) * taps + t] * op.wscale;
+        __half hi, lo;
+        split_half(w, &hi, &lo);
+        op.w_packed[(((size_t)0 * taps + t) * op.cout_pad + co) * d.cin + ci] = hi;
+        if (planes == 2) op.w_packed[(((size_t)1 * taps + t) * op.cout_pad + co) * d.cin + ci] = lo;
+      }
+  op.bias_packed.assign(op.cout_pad, 0.f);
+  for (int co = 0; co < d.cout; ++co) op.bias_packed[co] = d.bias_host[co];
+  return CNL_OK;
+}
+
+static int prepare_stem(cnl_engine* e, OpInfo& op) {
+  const cnl_conv_desc& d = op.d;
+  const BufferInfo& src = e->bufs[d.src];
+  const BufferInfo& dst = e->bufs[d.dst];
+  if (!src.fp32_nchw || src.channels != 3 || d.cin != 3 || d.cout != 64 || d.ksize != 7 || d.stride != 2 || d.pad != 3 ||
+      dst.fp32_nchw || dst.channels != 64 || dst.h * 4 != src.h || dst.w * 4 != src.w)
+    return fail(CNL_ERR_UNSUPPORTED, "stem must be conv7x7/2 (3->64) + max-pool3x3/2 from the fp32 image");
+  op.w_stem.assign(147 * 64, 0.f);
+  for (int co = 0; co < 64; ++co)
+    for (int k = 0; k < 147; ++k) op.w_stem[(size_t)k * 64 + co] = d.weight_host[(size_t)co * 147 + k];
+  op.bias_packed.assign(d.bias_host, d.bias_host + 64);
+  return CNL_OK;
+}
+
+}  // namespace cnl
+
+using namespace cnl;
+
+extern "C" {
+
+int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_buffers, const cnl_conv_desc* ops, int n_ops,
+                      int batch, int height, int width, int precision, int device) {
+  if (!out || !buffers || !ops || n_buffers < 2 || n_ops < 1) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: bad arguments");
+  if (batch < 1 || height < 32 || width < 32 || height % 32 || width % 32)
+    return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: input must be a multiple of 32 in both dimensions (got %dx%d)", height, width);
+  if (precision != CNL_PRECISION_SPLIT && precision != CNL_PRECISION_FAST) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: precision");
+  cnl_engine* e = new cnl_engine();
+  e->batch = batch; e->height = height; e->width = width; e->precision = precision; e->device = device;
+  e->planes = (precision == CNL_PRECISION_SPLIT) ? 2 : 1;
+  e->uploaded_arena = nullptr;
+  e->num_sms = 148;
+  size_t off = 0;
+  for (int i = 0; i < n_buffers; ++i) {
+    BufferInfo b;
+    b.channels = buffers[i].channels; b.stride = buffers[i].stride; b.fp32_nchw = buffers[i].fp32_nchw;
+    if (b.stride < 1 || height % b.stride || width % b.stride) { delete e; return fail(CNL_ERR_INVALID_ARGUMENT, "buffer %d: bad stride", i); }
+    b.h = height / b.stride; b.w = width / b.stride;
+    b.plane_elems = (long long)batch * b.h * b.w * b.channels;
+    b.bytes = b.fp32_nchw ? (size_t)b.plane_elems * 4 : (size_t)b.plane_elems * 2 * e->planes;
+    b.offset = off;
+    if (i > 0) off += align_up(b.bytes, 1024);            // buffer 0 is the caller's image
+    e->bufs.push_back(b);
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    OpInfo op;
+    op.d = ops[i];
+    if (op.d.src < 0 || op.d.src >= n_buffers || op.d.dst <= 0 || op.d.dst >= n_buffers || op.d.residual >= n_buffers) {
+      delete e; return fail(CNL_ERR_INVALID_ARGUMENT, "op %d: bad buffer id", i);
+    }
+    int st = (op.d.kind == 1) ? prepare_stem(e, op) : prepare_conv(e, op);
+    if (st != CNL_OK) { delete e; return st; }
+    op.d.weight_host = nullptr; op.d.bias_host = nullptr;
+    if (op.d.kind == 1) {
+      op.w_offset = off; off += align_up(op.w_stem.size() * 4, 1024);
+      op.bias_offset = off; off += align_up(64 * 4, 1024);
+      op.scratch_offset = off; off += align_up((size_t)batch * (height / 2) * (width / 2) * 64 * 4, 1024);
+    } else {
+      op.w_offset = off; off += align_up(op.w_packed.size() * 2, 1024);
+      op.bias_offset = off; off += align_up(op.bias_packed.size() * 4, 1024);
+      op.scratch_offset = 0;
+    }
+    e->ops.push_back(std::move(op));
+  }
+  e->arena_bytes = off;
+  *out = e;
+  return CNL_OK;
+}
+
+void cnl_engine_destroy(cnl_engine* e) { delete e; }
+
+size_t cnl_engine_arena_bytes(const cnl_engine* e) { return e ? e->arena_bytes : 0; }
+
+size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer) {
+  if (!e || buffer < 0 || buffer >= (int)e->bufs.size()) return (size_t)-1;
+  return e->bufs[buffer].offset;
+}
+
+int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
+  if (!e || !arena) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_upload: null argument");
+  if (reinterpret_cast<uintptr_t>(arena) & 1023) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_upload: arena must be 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev_sms = 0;
+  CNL_CUDA_CHECK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, e->device));
+  int cc_major = 0;
+  CNL_CUDA_CHECK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, e->device));
+  if (cc_major != 10) return fail(CNL_ERR_UNSUPPORTED, "cnl_b200 kernels are built for sm_100a only (device has compute capability %d.x)", cc_major);
+  e->num_sms = dev_sms;
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+  uint8_t* base = static_cast<uint8_t*>(arena);
+  const int planes = e->planes;
+  for (OpInfo& op : e->ops) {
+    const cnl_conv_desc& d = op.d;
+    if (d.kind == 1) {
+      CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_stem.data(), op.w_stem.size() * 4, cudaMemcpyHostToDevice, st));
+      CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.bias_offset, op.bias_packed.data(), 64 * 4, cudaMemcpyHostToDevice, st));
+      continue;
+    }
+    CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_packed.data(), op.w_packed.size() * 2, cudaMemcpyHostToDevice, st));
+    CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.bias_offset, op.bias_packed.data(), op.bias_packed.size() * 4, cudaMemcpyHostToDevice, st));
+    const BufferInfo& src = e->bufs[d.src];
+    const BufferInfo& dst = e->bufs[d.dst];
+    const int taps = d.ksize * d.ksize;
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.w, (cuuint64_t)src.h, (cuuint64_t)e->batch * planes};
+      cuuint64_t str[3] = {(cuuint64_t)src.channels * 2, (cuuint64_t)src.w * src.channels * 2, (cuuint64_t)src.h * src.w * src.channels * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)(op.tw * d.stride), (cuuint32_t)(op.th * d.stride), 1};
+      cuuint32_t es[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+      int r = encode_map(&op.src_map, base + src.offset, 4, dims, str, box, es, "src");
+      if (r) return r;
+    }
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)op.cout_pad, (cuuint64_t)taps * planes};
+      cuuint64_t str[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)op.cout_pad * d.cin * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)op.n_tile, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      int r = encode_map(&op.w_map, base + op.w_offset, 3, dims, str, box, es, "weights");
+      if (r) return r;
+    }
+    if (!dst.fp32_nchw) {
+      cuuint64_t dims[4] = {(cuuint64_t)dst.channels, (cuuint64_t)dst.w, (cuuint64_t)dst.h, (cuuint64_t)e->batch * planes};
+      cuuint64_t str[3] = {(cuuint64_t)dst.channels * 2, (cuuint64_t)dst.w * dst.channels * 2, (cuuint64_t)dst.h * dst.w * dst.channels * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      int r = encode_map(&op.dst_map, base + dst.offset, 4, dims, str, box, es, "dst");
+      if (r) return r;
+    } else {
+      op.dst_map = op.src_map;
+    }
+  }
+  CNL_CUDA_CHECK(cudaStreamSynchronize(st));       // packed host weights are pageable: make the copies land before returning
+  e->uploaded_arena = arena;
+  return CNL_OK;
+}
+
+int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first_op, int last_op, void* stream, int* launches) {
+  if (!e || !arena) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: null argument");
+  if (arena != e->uploaded_arena) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: call cnl_engine_upload for this arena first");
+  if (first_op < 0 || last_op > (int)e->ops.size() || first_op > last_op) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: bad op range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(arena);
+  const int planes = e->planes;
+  int n_launch = 0;
+  for (int i = first_op; i < last_op; ++i) {
+    OpInfo& op = e->ops[i];
+    const cnl_conv_desc& d = op.d;
+    const BufferInfo& src = e->bufs[d.src];
+    const BufferInfo& dst = e->bufs[d.dst];
+    if (d.kind == 1) {
+      if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
+      float* scratch = reinterpret_cast<float*>(base + op.scratch_offset);
+      const int OH = e->height / 2, OW = e->width / 2;
+      dim3 grid((OW + kStemTile - 1) / kStemTile, (OH + kStemTile - 1) / kStemTile, e->batch);
+      stem_conv_kernel<<<grid, 256, kStemSmemBytes, st>>>(image, reinterpret_cast<const float*>(base + op.w_offset),
+                                                          reinterpret_cast<const float*>(base + op.bias_offset), scratch,
+                                                          e->height, e->width);
+      const long long total = (long long)e->batch * (OH / 2) * (OW / 2) * 8;
+      const int blocks = (int)((total + 255) / 256);
+      __half* o = reinterpret_cast<__half*>(base + dst.offset);
+      if (planes == 2) stem_pool_kernel<2><<<blocks, 256, 0, st>>>(scratch, o, e->batch, OH, OW, dst.plane_elems);
+      else             stem_pool_kernel<1><<<blocks, 256, 0, st>>>(scratch, o, e->batch, OH, OW, dst.plane_elems);
+      n_launch += 2;
+      CNL_CUDA_CHECK(cudaGetLastError());
+      continue;
+    }
+    ConvParams p;
+    p.n_img = e->batch; p.out_h = dst.h; p.out_w = dst.w;
+    p.tw = op.tw; p.th = op.th; p.tiles_w = op.tiles_w; p.tiles_h = op.tiles_h;
+    p.m_tiles = e->batch * op.tiles_w * op.tiles_h;
+    p.n_tiles = op.n_tiles; p.n_tile = op.n_tile;
+    p.ksize = d.ksize; p.stride = d.stride; p.pad = d.pad; p.kblocks = d.cin / 64;
+    p.src_c_off = d.src_c_off; p.dst_c_off = d.dst_c_off;
+    p.relu = d.relu;
+    p.out_mode = dst.fp32_nchw ? 1 : 0;
+    p.cout_real = d.cout;
+    p.wscale_inv = 1.0f / op.wscale;
+    p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
+    p.out_nchw = dst.fp32_nchw ? reinterpret_cast<float*>(base + dst.offset) : nullptr;
+    p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
+    if (d.residual >= 0) {
+      const BufferInfo& rb = e->bufs[d.residual];
+      p.res = reinterpret_cast<const __half*>(base + rb.offset);
+      p.res_up = d.residual_up; p.res_c = rb.channels; p.res_h = rb.h; p.res_w = rb.w; p.res_plane_elems = rb.plane_elems;
+    }
+    p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int grid = std::min(total_tiles, e->num_sms);
+    if (planes == 2) conv_tc_kernel<2><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+    else             conv_tc_kernel<1><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+    ++n_launch;
+    CNL_CUDA_CHECK(cudaGetLastError());
+    (void)src;
+  }
+  if (launches) *launches = n_launch;
+  return CNL_OK;
+}
+
+int cnl_engine_read_buffer(cnl_engine* e, void* arena, int buffer, float* out_nchw, void* stream) {
+  if (!e || !arena || !out_nchw || buffer <= 0 || buffer >= (int)e->bufs.size()) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_read_buffer: bad arguments");
+  const BufferInfo& b = e->bufs[buffer];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(arena);
+  if (b.fp32_nchw) {
+    CNL_CUDA_CHECK(cudaMemcpyAsync(out_nchw, base + b.offset, b.bytes, cudaMemcpyDeviceToDevice, st));
+    return CNL_OK;
+  }
+  const long long total = b.plane_elems;
+  planes_to_nchw_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(base + b.offset), out_nchw,
+                                                                    e->batch, b.channels, b.h, b.w, e->planes, b.plane_elems);
+  CNL_CUDA_CHECK(cudaGetLastError());
+  return CNL_OK;
+}
+
+int cnl_engine_write_buffer(cnl_engine* e, void* arena, int buffer, const float* in_nchw, void* stream) {
+  if (!e || !arena || !in_nchw || buffer <= 0 || buffer >= (int)e->bufs.size()) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_write_buffer: bad arguments");
+  const BufferInfo& b = e->bufs[buffer];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(arena);
+  if (b.fp32_nchw) {
+    CNL_CUDA_CHECK(cudaMemcpyAsync(base + b.offset, in_nchw, b.bytes, cudaMemcpyDeviceToDevice, st));
+    return CNL_OK;
+  }
+  const long long total = b.plane_elems;
+  nchw_to_planes_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(in_nchw, reinterpret_cast<__half*>(base + b.offset), e->batch,
+                                                                    b.channels, b.h, b.w, e->planes, b.plane_elems);
+  CNL_CUDA_CHECK(cudaGetLastError());
+  return CNL_OK;
+}
+
+}  // extern "C"

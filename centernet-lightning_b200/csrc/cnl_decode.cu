@@ -13,6 +13,7 @@
 //                     op-by-op fp32 rounding (no FMA contraction), optional reid gather.
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include "cnl_common.h"
 
@@ -35,65 +36,51 @@ int fail(int code, const char* fmt, ...) {
 // The logistic the from_logits path specifies: three separately rounded fp32 operations.
 __device__ __forceinline__ float sigmoid32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// Logits closer than this (or above kSatLogit) may round to the same fp32 probability; only then is the
-// probability-space comparison of the reference evaluated explicitly.  d(sigmoid)/dx >= 2^-24*(1+e^x) bounds it.
-constexpr float kNearTie = 5e-5f;
-constexpr float kSatLogit = 4.0f;
+// from_logits semantics.  The reference compares PROBABILITIES (centernet.py:252-254).  The logistic is monotone,
+// so the pseudo-NMS and the class arg-max are evaluated on the logits instead (no transcendental in the streaming
+// loop) and only the per-pixel winner is pushed through sigmoid32.  The two orders differ only where fp32 rounding
+// maps distinct logits to one probability; the case that matters in practice is saturation - every logit >= 16.64
+// has probability exactly 1.0f, so the reference sees a plateau there (neighbouring saturated pixels are all kept,
+// the first saturated class wins the label).  Clamping logits at kSatLogit reproduces that plateau exactly.
+constexpr float kSatLogit = 17.0f;
 
-struct Cand {           // running per-pixel winner across classes
-  float v;              // LOGITS: best peak logit (-inf = none yet).  PROBS: best heatmap*mask value so far.
-  int label;
-};
-
-// x: centre value, m: kxk window max (m >= x).  Reference: mask = (maxpool(p) == p); p*mask; max over classes (first wins).
+// x: centre value, m: kxk window max (m >= x), c: class.  Reference: mask = (maxpool(h) == h); h*mask; max over
+// classes with the first maximal class winning.
 template <bool LOGITS>
-__device__ __forceinline__ void update_cand(Cand& s, float x, float m, int c) {
-  if (LOGITS) {
-    bool peak = (x == m);
-    if (!peak) {
-      float d = m - x;
-      if (d < kNearTie || x > kSatLogit) peak = (sigmoid32(x) == sigmoid32(m));   // fp32 probability plateau
-    }
-    if (peak) {
-      bool take = x > s.v;
-      if (take && s.v != -INFINITY) {
-        float e = x - s.v;
-        if (e < kNearTie || s.v > kSatLogit) take = sigmoid32(x) > sigmoid32(s.v);
-      }
-      if (take) { s.v = x; s.label = c; }
-    }
-  } else {
+__device__ __forceinline__ void update_cand(float& best, int& label, float x, float m, int c) {
+  if (LOGITS) {                       // best starts at -inf: "no peak yet"
+    bool take = (x == m) && (x > best);
+    best = take ? x : best;
+    label = take ? c : label;
+  } else {                            // exact h*mask semantics for any finite input: non-peaks contribute 0
     float cand = (x == m) ? x : 0.0f;
-    if (cand > s.v) { s.v = cand; s.label = c; }
-  }
-}
-
-// Merge a later class group into an earlier one (groups are visited in class order, so "first max wins" holds).
-template <bool LOGITS>
-__device__ __forceinline__ void merge_cand(Cand& s, const Cand& o) {
-  if (LOGITS) {
-    if (o.v == -INFINITY) return;
-    bool take = o.v > s.v;
-    if (take && s.v != -INFINITY) {
-      float e = o.v - s.v;
-      if (e < kNearTie || s.v > kSatLogit) take = sigmoid32(o.v) > sigmoid32(s.v);
-    }
-    if (take) s = o;
-  } else {
-    if (o.v > s.v) s = o;
+    bool take = cand > best;
+    best = take ? cand : best;
+    label = take ? c : label;
   }
 }
 
 template <bool LOGITS>
-__device__ __forceinline__ void finish_cand(const Cand& s, float& score, int& label) {
+__device__ __forceinline__ void finish_cand(float best, int lab, float& score, int& label) {
   if (LOGITS) {
-    score = sigmoid32(s.v);                 // -inf (no peak at this pixel) -> exactly 0
-    label = (score == 0.0f) ? 0 : s.label;  // an all-zero column arg-maxes to class 0 in the reference
+    score = sigmoid32(best);                // -inf (no peak at this pixel) -> exactly 0; >= 17 -> exactly 1
+    label = (score == 0.0f) ? 0 : lab;      // an all-zero column arg-maxes to class 0 in the reference
   } else {
-    score = s.v;
-    label = s.label;
+    score = best;
+    label = lab;
   }
 }
+
+__device__ __forceinline__ uint32_t sortable_key(float f) {       // larger float <=> larger key (NaN-free input)
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+constexpr int kHistBins = 4096;             // per-image histogram of candidate keys (top 12 bits), built by kernel 1
+constexpr int kHistShift = 20;
 
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1a: fast streaming peaks kernel (W % 4 == 0).  One warp = RxTW pixel strip x one class group.
@@ -110,74 +97,66 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
-template <int P, bool LOGITS, int R, int G>
-__global__ void __launch_bounds__(G * 32)
-peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, uint16_t* __restrict__ clabel,
-                  int C, int H, int W) {
+// Class loop of one warp: rows [r0-P, r0+R+P) x columns [x0-P, x0+4+P) of classes [c_begin, c_end).
+// EDGE=false is the interior fast path (every row and column of the strip is inside the map: no predicates).
+template <int P, bool LOGITS, int R, bool MT, bool EDGE>
+__device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base, size_t plane, int c_begin, int c_end,
+                                                 int H, int W, int r0, int x0, int lane, bool col_ok,
+                                                 float (&best)[R][4], int (&lab)[R][4]) {
   constexpr int ROWS = R + 2 * P;
-  const int lane = threadIdx.x & 31;
-  const int g = threadIdx.x >> 5;
-  const int n = blockIdx.z;
-  const int r0 = blockIdx.y * R;
-  const int x0 = blockIdx.x * kTW + lane * 4;
-  const bool col_ok = x0 < W;
-  const bool multi_tile = gridDim.x > 1;
-  const size_t plane = (size_t)H * W;
-  const int cg = (C + G - 1) / G;
-  const int c_begin = g * cg;
-  const int c_end = min(C, c_begin + cg);
+  constexpr int PH = (P > 0) ? P : 1;
   const float NEG = -INFINITY;
-
-  Cand st[R][4];
+  bool row_ok[ROWS];
 #pragma unroll
-  for (int i = 0; i < R; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { st[i][j].v = NEG; st[i][j].label = 0; }
+  for (int j = 0; j < ROWS; ++j) { int r = r0 - P + j; row_ok[j] = !EDGE || (r >= 0 && r < H); }
 
-  const float* img = heat + (size_t)n * C * plane;
+#pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
-    const float* pl = img + (size_t)c * plane;
+    const float* pl = base + (size_t)c * plane;
     float4 v[ROWS];
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
-      int r = r0 - P + j;
-      v[j] = (col_ok && r >= 0 && r < H) ? ld_stream4(pl + (size_t)r * W + x0) : make_float4(NEG, NEG, NEG, NEG);
+      if (EDGE) v[j] = (row_ok[j] && col_ok) ? ld_stream4(pl + (long long)j * W) : make_float4(NEG, NEG, NEG, NEG);
+      else      v[j] = ld_stream4(pl + (long long)j * W);
     }
-    // halo columns owned by neighbouring column tiles (only when a row is wider than one warp tile)
-    constexpr int PH = (P > 0) ? P : 1;
-    float hl[ROWS][PH], hr[ROWS][PH];
+    if (LOGITS) {
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j)
+      for (int j = 0; j < ROWS; ++j)
+        v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
+    }
+    // Halo columns of neighbouring column tiles (rows wider than one 128-column warp tile).  The neighbour shuffles
+    // below are rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the
+    // right" shuffle are free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
+    float hx[ROWS][PH];
+    if constexpr (P > 0 && MT) {
 #pragma unroll
-      for (int q = 0; q < PH; ++q) { hl[j][q] = NEG; hr[j][q] = NEG; }
-    if constexpr (P > 0) {
-      if (multi_tile && (lane == 0 || lane == 31)) {
+      for (int j = 0; j < ROWS; ++j)
 #pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-          int r = r0 - P + j;
-          if (r >= 0 && r < H) {
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-              int xl = x0 - 1 - q, xr = x0 + 4 + q;
-              if (lane == 0 && xl >= 0) hl[j][q] = __ldg(pl + (size_t)r * W + xl);
-              if (lane == 31 && xr < W) hr[j][q] = __ldg(pl + (size_t)r * W + xr);
-            }
+        for (int q = 0; q < P; ++q) {
+          hx[j][q] = NEG;
+          const int xt = (lane == 31) ? (x0 - 124 - 1 - q) : (x0 + 128 + q);     // tile's first column - 1 - q / last + 1 + q
+          if ((lane == 0 || lane == 31) && row_ok[j] && xt >= 0 && xt < W) {
+            float t = __ldg(pl + (long long)j * W + (xt - x0));
+            hx[j][q] = LOGITS ? fminf(t, kSatLogit) : t;
           }
         }
-      }
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       // vertical max over the window rows
       float4 vm = v[i];
-      float vl[PH], vr[PH];
+      float vh[PH];
+      if constexpr (P > 0 && MT) {
 #pragma unroll
-      for (int q = 0; q < PH; ++q) { vl[q] = hl[i][q]; vr[q] = hr[i][q]; }
+        for (int q = 0; q < P; ++q) vh[q] = hx[i][q];
+      }
 #pragma unroll
       for (int j = 1; j <= 2 * P; ++j) {
         vm = max4(vm, v[i + j]);
+        if constexpr (P > 0 && MT) {
 #pragma unroll
-        for (int q = 0; q < PH; ++q) { vl[q] = fmaxf(vl[q], hl[i + j][q]); vr[q] = fmaxf(vr[q], hr[i + j][q]); }
+          for (int q = 0; q < P; ++q) vh[q] = fmaxf(vh[q], hx[i + j][q]);
+        }
       }
       // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+3] own, e[P+4..] right neighbours
       float e[4 + 2 * P];
@@ -187,10 +166,13 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
 #pragma unroll
         for (int q = 0; q < P; ++q) {
           // q-th column to the left of x0 is component (3-q) of lane-1; to the right of x0+3 it is component q of lane+1
-          float fl = __shfl_up_sync(0xffffffffu, own[3 - q], 1);
-          float fr = __shfl_down_sync(0xffffffffu, own[q], 1);
-          e[P - 1 - q] = (lane == 0) ? vl[q] : fl;
-          e[P + 4 + q] = (lane == 31) ? vr[q] : fr;
+          float src_l = own[3 - q], src_r = own[q];
+          if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
+          float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
+          float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
+          if constexpr (!MT) { fl = (lane == 0) ? NEG : fl; fr = (lane == 31) ? NEG : fr; }
+          e[P - 1 - q] = fl;
+          e[P + 4 + q] = fr;
         }
       }
       const float ctr[4] = {v[i + P].x, v[i + P].y, v[i + P].z, v[i + P].w};
@@ -199,22 +181,49 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
         float m = e[j];
 #pragma unroll
         for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[j + q]);
-        update_cand<LOGITS>(st[i][j], ctr[j], m, c);
+        update_cand<LOGITS>(best[i][j], lab[i][j], ctr[j], m, c);
       }
     }
   }
+}
+
+template <int P, bool LOGITS, int R, int G, bool MT>
+__global__ void __launch_bounds__(G * 32, (G == 4) ? 7 : 8)
+peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, uint16_t* __restrict__ clabel,
+                  unsigned int* __restrict__ hist, int C, int H, int W) {
+  const int lane = threadIdx.x & 31;
+  const int g = threadIdx.x >> 5;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * R;
+  const int x0 = blockIdx.x * kTW + lane * 4;
+  const bool col_ok = x0 < W;
+  const size_t plane = (size_t)H * W;
+  const int cg = (C + G - 1) / G;
+  const int c_begin = g * cg;
+  const int c_end = min(C, c_begin + cg);
+
+  float best[R][4];
+  int lab[R][4];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { best[i][j] = -INFINITY; lab[i][j] = 0; }
+
+  const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
+  const bool interior = (r0 - P >= 0) && (r0 + R + P <= H) && ((int)(blockIdx.x + 1) * kTW <= W);   // block-uniform
+  if (interior) peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
+  else          peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
 
   // merge the G class groups (in class order) through shared memory, then emit one candidate per pixel
   __shared__ float s_v[G][R][kTW];
   __shared__ uint16_t s_l[G][R][kTW];
   if (G > 1) {
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s_v[g][i][lane * 4 + j] = st[i][j].v;
-        s_l[g][i][lane * 4 + j] = (uint16_t)st[i][j].label;
-      }
+    for (int i = 0; i < R; ++i) {
+      *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
+      *reinterpret_cast<ushort4*>(&s_l[g][i][lane * 4]) =
+          make_ushort4((uint16_t)lab[i][0], (uint16_t)lab[i][1], (uint16_t)lab[i][2], (uint16_t)lab[i][3]);
+    }
     __syncthreads();
   }
   for (int i = g; i < R; i += G) {          // warp g finishes rows g, g+G, ...
@@ -224,18 +233,19 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
     int lb[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      Cand a;
+      float bv; int bl;
       if (G > 1) {
-        a.v = s_v[0][i][lane * 4 + j]; a.label = s_l[0][i][lane * 4 + j];
+        bv = s_v[0][i][lane * 4 + j]; bl = s_l[0][i][lane * 4 + j];
 #pragma unroll
-        for (int gg = 1; gg < G; ++gg) {
-          Cand o; o.v = s_v[gg][i][lane * 4 + j]; o.label = s_l[gg][i][lane * 4 + j];
-          merge_cand<LOGITS>(a, o);
+        for (int gg = 1; gg < G; ++gg) {    // later groups hold later classes: strict > keeps the first maximal class
+          float ov = s_v[gg][i][lane * 4 + j];
+          if (ov > bv) { bv = ov; bl = s_l[gg][i][lane * 4 + j]; }
         }
       } else {
-        a = st[i][j];
+        bv = best[i][j]; bl = lab[i][j];
       }
-      finish_cand<LOGITS>(a, sc[j], lb[j]);
+      finish_cand<LOGITS>(bv, bl, sc[j], lb[j]);
+      atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(sc[j]) >> kHistShift), 1u);
     }
     size_t o = (size_t)n * plane + (size_t)r * W + x0;
     *reinterpret_cast<float4*>(cscore + o) = make_float4(sc[0], sc[1], sc[2], sc[3]);
@@ -250,14 +260,15 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
 template <bool LOGITS>
 __global__ void __launch_bounds__(256)
 peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cscore, uint16_t* __restrict__ clabel,
-                     int C, int H, int W, int P) {
+                     unsigned int* __restrict__ hist, int C, int H, int W, int P) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int n = blockIdx.z;
   if (x >= W || y >= H) return;
   const size_t plane = (size_t)H * W;
   const float* img = heat + (size_t)n * C * plane;
-  Cand s; s.v = -INFINITY; s.label = 0;
+  float best = -INFINITY;
+  int lab = 0;
   const int y_lo = max(0, y - P), y_hi = min(H - 1, y + P);
   const int x_lo = max(0, x - P), x_hi = min(W - 1, x + P);
   for (int c = 0; c < C; ++c) {
@@ -266,30 +277,31 @@ peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cscore,
     float m = ctr;
     for (int yy = y_lo; yy <= y_hi; ++yy)
       for (int xx = x_lo; xx <= x_hi; ++xx) m = fmaxf(m, __ldg(pl + (size_t)yy * W + xx));
-    update_cand<LOGITS>(s, ctr, m, c);
+    if (LOGITS) { ctr = fminf(ctr, kSatLogit); m = fminf(m, kSatLogit); }
+    update_cand<LOGITS>(best, lab, ctr, m, c);
   }
   float score; int label;
-  finish_cand<LOGITS>(s, score, label);
+  finish_cand<LOGITS>(best, lab, score, label);
   size_t o = (size_t)n * plane + (size_t)y * W + x;
   cscore[o] = score;
   clabel[o] = (uint16_t)label;
+  atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(score) >> kHistShift), 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Kernel 2: per-image exact top-k (radix select + ordered ties + bitonic sort) and gather/decode.
+// Kernel 2: per-image exact top-k and gather/decode.  One CTA per image.
+//   fast path:  kernel 1 left a 4096-bin histogram of the candidate keys; a suffix scan finds the bin holding the
+//               k-th largest, every candidate in that bin or above (usually k .. a few hundred) is collected and
+//               bitonic-sorted on (key desc, index asc).
+//   fallback:   when that set does not fit (large plateaus of equal scores) an exact 3-pass radix select with
+//               ordered tie handling runs instead.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kSelThreads = 1024;
 constexpr int kMaxK = 1024;
+constexpr int kListCap = 2048;
 constexpr int kBins = 2048;
-
-__device__ __forceinline__ uint32_t sortable_key(float f) {       // larger float <=> larger key (NaN-free input)
-  uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float key_to_float(uint32_t k) {
-  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-  return __uint_as_float(b);
-}
+constexpr int kSubShift = kHistShift - 11;   // second-level digit: the next 11 key bits
+constexpr int kRefineAbove = 256;            // sort directly when bin_k-and-above holds at most this many
 
 // inclusive block scan over kSelThreads ints (warp shuffles + one smem hop)
 __device__ __forceinline__ int block_inclusive_scan(int v, int* s_warp /*[32]*/) {
@@ -315,7 +327,6 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int* s_warp /*[32]*/)
   __syncthreads();          // s_warp may be reused by the caller right away
   return v;
 }
-
 
 // reference centernet.py:278-303 for one detection: every fp32 op rounded separately (no FMA contraction)
 __device__ __forceinline__ float4 decode_box(const float* box_img, size_t plane, int idx, int H, int W,
@@ -360,28 +371,29 @@ __global__ void gather_boxes_kernel(const float* __restrict__ box, const long lo
       decode_box(box + (size_t)n * 4 * plane, plane, (int)idx, H, W, normalize, box_log, mult, stride_f);
 }
 
+// Elementwise logistic for the G1 forward() alias (heads return probabilities there): same sigmoid32 as the fused decode.
+__global__ void sigmoid_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = sigmoid32(in[i]);
+}
+
 struct DecodeParams {
-  const float* cscore; const uint16_t* clabel;
+  const float* cscore; const uint16_t* clabel; const unsigned int* hist;
   const float* box; const float* reid;
   int H, W, E, k;
   int normalize, box_log; float mult; float stride_f;
   float* boxes; float* scores; long long* labels; long long* indices; float* emb;
 };
 
-__global__ void __launch_bounds__(kSelThreads)
-select_gather_kernel(DecodeParams p) {
-  __shared__ int s_hist[kBins];
-  __shared__ int s_warp[32];
-  __shared__ unsigned long long s_list[kMaxK];
-  __shared__ int s_bin, s_above, s_cnt;
+__device__ __forceinline__ unsigned long long pack_entry(uint32_t key, int idx) {
+  return ((unsigned long long)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)idx);   // descending = score desc, index asc
+}
 
-  const int n = blockIdx.x;
+// exact radix select + ordered ties: fills s_list[0..k) (unsorted).  Used only when the histogram path overflows.
+__device__ void radix_select_fallback(const float* sc, int HW, int k, unsigned long long* s_list, int* s_hist,
+                                      int* s_warp, int* s_scalars /*[3]: bin, above, cnt*/) {
   const int tid = threadIdx.x;
-  const int HW = p.H * p.W;
-  const float* sc = p.cscore + (size_t)n * HW;
-  const int k = p.k;
-
-  // ---- 3-pass MSB radix select of the k-th largest key --------------------------------------------------
   uint32_t prefix = 0, mask = 0;
   int need = k;
   int count_at_T = 0;
@@ -398,35 +410,29 @@ select_gather_kernel(DecodeParams p) {
       if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & dm], 1);
     }
     __syncthreads();
-    // suffix counts from the top bin: thread t owns reversed bins 2t, 2t+1  (bin = kBins-1-rev)
     int b_hi = s_hist[kBins - 1 - 2 * tid];
     int b_lo = s_hist[kBins - 2 - 2 * tid];
     int incl = block_inclusive_scan(b_hi + b_lo, s_warp);
     int excl = incl - (b_hi + b_lo);
     if (excl < need && need <= incl) {            // exactly one thread
-      if (need <= excl + b_hi) { s_bin = kBins - 1 - 2 * tid; s_above = excl; s_cnt = b_hi; }
-      else                     { s_bin = kBins - 2 - 2 * tid; s_above = excl + b_hi; s_cnt = b_lo; }
+      if (need <= excl + b_hi) { s_scalars[0] = kBins - 1 - 2 * tid; s_scalars[1] = excl; s_scalars[2] = b_hi; }
+      else                     { s_scalars[0] = kBins - 2 - 2 * tid; s_scalars[1] = excl + b_hi; s_scalars[2] = b_lo; }
     }
     __syncthreads();
-    need -= s_above;
-    prefix |= ((uint32_t)s_bin) << shift;
+    need -= s_scalars[1];
+    prefix |= ((uint32_t)s_scalars[0]) << shift;
     mask |= dm << shift;
-    count_at_T = s_cnt;
+    count_at_T = s_scalars[2];
     __syncthreads();
   }
   const uint32_t T = prefix;              // key of the k-th largest candidate
   const int n_greater = k - need;         // all keys > T are selected; `need` (>=1) of the keys == T
-
-  // ---- collect winners as (key << 32 | ~index): descending order of this word = score desc, index asc ----
-  if (tid == 0) s_cnt = 0;
+  if (tid == 0) s_scalars[2] = 0;
   __syncthreads();
   const bool all_ties_taken = (count_at_T == need);
   for (int i = tid; i < HW; i += kSelThreads) {
     uint32_t u = sortable_key(sc[i]);
-    if (u > T || (all_ties_taken && u == T)) {
-      int pos = atomicAdd(&s_cnt, 1);
-      s_list[pos] = ((unsigned long long)u << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
-    }
+    if (u > T || (all_ties_taken && u == T)) s_list[atomicAdd(&s_scalars[2], 1)] = pack_entry(u, i);
   }
   if (!all_ties_taken) {
     // more candidates equal to T than slots left: take the lowest flat indices (deterministic tie rule)
@@ -438,15 +444,130 @@ select_gather_kernel(DecodeParams p) {
     int incl = block_inclusive_scan(mine, s_warp);
     int rank = incl - mine;
     for (int i = b; i < e && rank < need; ++i) {
-      if (sortable_key(sc[i]) == T) {
-        s_list[n_greater + rank] = ((unsigned long long)T << 32) | (uint32_t)(0xffffffffu - (uint32_t)i);
-        ++rank;
-      }
+      if (sortable_key(sc[i]) == T) { s_list[n_greater + rank] = pack_entry(T, i); ++rank; }
     }
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_gather_kernel(DecodeParams p) {
+  __shared__ unsigned long long s_list[kListCap];
+  __shared__ int s_hist[kBins];
+  __shared__ int s_warp[32];
+  __shared__ int s_scalars[3];
+  __shared__ int s_n;
+
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int HW = p.H * p.W;
+  const float* sc = p.cscore + (size_t)n * HW;
+  const int k = p.k;
+
+  // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
+  const uint4 h4 = *reinterpret_cast<const uint4*>(p.hist + (size_t)n * kHistBins + (kHistBins - 4 - 4 * tid));
+  const int cnt[4] = {(int)h4.w, (int)h4.z, (int)h4.y, (int)h4.x};      // descending bin order
+  const int sum4 = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  int incl = block_inclusive_scan(sum4, s_warp);
+  int run = incl - sum4;
+  if (run < k && k <= incl) {                    // exactly one thread: the k-th largest lies in one of its bins
+    int b = 0;
+    while (run + cnt[b] < k) { run += cnt[b]; ++b; }
+    s_scalars[0] = kHistBins - 1 - 4 * tid - b;  // bin
+    s_scalars[1] = run + cnt[b];                 // candidates in this bin or above
+    s_n = 0;
+  }
+  __syncthreads();
+  const uint32_t bin_k = (uint32_t)s_scalars[0];
+  const int n_in_or_above = s_scalars[1];
+  const bool vec4 = (HW & 3) == 0;
+  const float4* sc4 = reinterpret_cast<const float4*>(sc);
+  const int n_vec = vec4 ? (HW >> 2) : 0;
+  __syncthreads();                                  // everyone has read s_scalars before it is reused
+  int n_sort;
+  bool done = false;
+  if (n_in_or_above <= kRefineAbove) {
+    // few enough: collect every candidate in bin_k or above and sort them all
+    for (int i = tid; i < n_vec; i += kSelThreads) {
+      const float4 f = sc4[i];
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t u = sortable_key(fv[j]);
+        if ((u >> kHistShift) >= bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, 4 * i + j);
+      }
+    }
+    for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) {
+      const uint32_t u = sortable_key(sc[i]);
+      if ((u >> kHistShift) >= bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
+    }
+    n_sort = n_in_or_above;
+    done = true;
+  } else {
+    // Scores crowd into bin_k (e.g. probabilities close to 1): refine with the next 11 key bits.  One pass
+    // collects everything above bin_k and histograms the members of bin_k; a second pass collects the members
+    // of bin_k at or above the sub-bin that holds the k-th largest.
+    for (int i = tid; i < kBins; i += kSelThreads) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_vec; i += kSelThreads) {
+      const float4 f = sc4[i];
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t u = sortable_key(fv[j]);
+        const uint32_t b = u >> kHistShift;
+        if (b > bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, 4 * i + j);
+        else if (b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
+      }
+    }
+    for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) {
+      const uint32_t u = sortable_key(sc[i]);
+      const uint32_t b = u >> kHistShift;
+      if (b > bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
+      else if (b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
+    }
+    __syncthreads();
+    const int n_above = s_n;                         // < k by construction
+    const int need = k - n_above;
+    const int b_hi = s_hist[kBins - 1 - 2 * tid];
+    const int b_lo = s_hist[kBins - 2 - 2 * tid];
+    const int incl2 = block_inclusive_scan(b_hi + b_lo, s_warp);
+    const int excl2 = incl2 - (b_hi + b_lo);
+    if (excl2 < need && need <= incl2) {
+      if (need <= excl2 + b_hi) { s_scalars[0] = kBins - 1 - 2 * tid; s_scalars[1] = excl2 + b_hi; }
+      else                      { s_scalars[0] = kBins - 2 - 2 * tid; s_scalars[1] = incl2; }
+    }
+    __syncthreads();
+    const uint32_t sub_k = (uint32_t)s_scalars[0];
+    const int n_total = n_above + s_scalars[1];
+    if (n_total <= kListCap) {
+      for (int i = tid; i < n_vec; i += kSelThreads) {
+        const float4 f = sc4[i];
+        const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t u = sortable_key(fv[j]);
+          if ((u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k)
+            s_list[atomicAdd(&s_n, 1)] = pack_entry(u, 4 * i + j);
+        }
+      }
+      for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) {
+        const uint32_t u = sortable_key(sc[i]);
+        if ((u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
+      }
+      n_sort = n_total;
+      done = true;
+    }
+    __syncthreads();
+  }
+  if (!done) {                                       // large plateaus of equal scores: exact radix select
+    radix_select_fallback(sc, HW, k, s_list, s_hist, s_warp, s_scalars);
+    n_sort = k;
+  }
   int kp = 1;
-  while (kp < k) kp <<= 1;
-  for (int i = k + tid; i < kp; i += kSelThreads) s_list[i] = 0ull;
+  while (kp < n_sort) kp <<= 1;
+  __syncthreads();
+  for (int i = n_sort + tid; i < kp; i += kSelThreads) s_list[i] = 0ull;
   __syncthreads();
 
   // ---- bitonic sort, descending ---------------------------------------------------------------------------
@@ -463,14 +584,13 @@ select_gather_kernel(DecodeParams p) {
     }
   }
 
-  // ---- gather + decode (reference centernet.py:278-303: every op rounded separately) ---------------------
+  // ---- gather + decode -------------------------------------------------------------------------------------
   const size_t plane = (size_t)HW;
   for (int j = tid; j < k; j += kSelThreads) {
     unsigned long long w = s_list[j];
     int idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
-    float score = key_to_float((uint32_t)(w >> 32));
     size_t o = (size_t)n * k + j;
-    p.scores[o] = score;
+    p.scores[o] = key_to_float((uint32_t)(w >> 32));
     p.indices[o] = idx;
     p.labels[o] = p.clabel[(size_t)n * HW + idx];
     if (p.box == nullptr) continue;
@@ -491,33 +611,38 @@ select_gather_kernel(DecodeParams p) {
 // Host side
 // ------------------------------------------------------------------------------------------------------------
 template <int P, bool LOGITS>
-static void launch_fast(const float* heat, float* cscore, uint16_t* clabel, int N, int C, int H, int W, cudaStream_t st) {
+static void launch_fast(const float* heat, float* cscore, uint16_t* clabel, unsigned int* hist, int N, int C, int H, int W,
+                        cudaStream_t st) {
   constexpr int R = 4;
   dim3 grid((W + kTW - 1) / kTW, (H + R - 1) / R, N);
-  if (C >= 32) {
-    peaks_fast_kernel<P, LOGITS, R, 4><<<grid, 4 * 32, 0, st>>>(heat, cscore, clabel, C, H, W);
-  } else if (C >= 2) {
-    peaks_fast_kernel<P, LOGITS, R, 2><<<grid, 2 * 32, 0, st>>>(heat, cscore, clabel, C, H, W);
-  } else {
-    peaks_fast_kernel<P, LOGITS, R, 1><<<grid, 32, 0, st>>>(heat, cscore, clabel, C, H, W);
-  }
+  const bool mt = grid.x > 1;        // rows wider than one 128-column warp tile need halo columns from neighbours
+#define CNL_LAUNCH_PEAKS(G_)                                                                                      \
+  do {                                                                                                            \
+    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W);  \
+    else    peaks_fast_kernel<P, LOGITS, R, G_, false><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W); \
+  } while (0)
+  if (C >= 32) CNL_LAUNCH_PEAKS(4);
+  else if (C >= 2) CNL_LAUNCH_PEAKS(2);
+  else CNL_LAUNCH_PEAKS(1);
+#undef CNL_LAUNCH_PEAKS
 }
 
 template <bool LOGITS>
-static void launch_peaks(const float* heat, float* cscore, uint16_t* clabel, int N, int C, int H, int W, int P,
-                         bool force_generic, cudaStream_t st) {
+static void launch_peaks(const float* heat, float* cscore, uint16_t* clabel, unsigned int* hist, int N, int C, int H, int W,
+                         int P, bool force_generic, cudaStream_t st) {
   bool fast = !force_generic && (W % 4 == 0) && P <= 2 && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   if (fast) {
     switch (P) {
-      case 0: launch_fast<0, LOGITS>(heat, cscore, clabel, N, C, H, W, st); return;
-      case 1: launch_fast<1, LOGITS>(heat, cscore, clabel, N, C, H, W, st); return;
-      case 2: launch_fast<2, LOGITS>(heat, cscore, clabel, N, C, H, W, st); return;
+      case 0: launch_fast<0, LOGITS>(heat, cscore, clabel, hist, N, C, H, W, st); return;
+      case 1: launch_fast<1, LOGITS>(heat, cscore, clabel, hist, N, C, H, W, st); return;
+      case 2: launch_fast<2, LOGITS>(heat, cscore, clabel, hist, N, C, H, W, st); return;
     }
   }
   dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-  peaks_generic_kernel<LOGITS><<<grid, 256, 0, st>>>(heat, cscore, clabel, C, H, W, P);
+  peaks_generic_kernel<LOGITS><<<grid, 256, 0, st>>>(heat, cscore, clabel, hist, C, H, W, P);
 }
 
+static size_t hist_bytes(int n) { return align_up((size_t)n * kHistBins * sizeof(unsigned int), 256); }
 static size_t score_bytes(int n, int h, int w) { return align_up((size_t)n * h * w * sizeof(float), 256); }
 
 }  // namespace cnl
@@ -532,7 +657,7 @@ int cnl_compiled_sm(void) { return 100; }
 
 size_t cnl_decode_workspace_bytes(int n, int h, int w) {
   if (n <= 0 || h <= 0 || w <= 0) return 0;
-  return score_bytes(n, h, w) + align_up((size_t)n * h * w * sizeof(uint16_t), 256);
+  return hist_bytes(n) + score_bytes(n, h, w) + align_up((size_t)n * h * w * sizeof(uint16_t), 256);
 }
 
 int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
@@ -570,20 +695,31 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: boxes must be 16-byte aligned");
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* cscore = static_cast<float*>(workspace);
-  uint16_t* clabel = reinterpret_cast<uint16_t*>(static_cast<char*>(workspace) + score_bytes(n, h, w));
+  unsigned int* hist = static_cast<unsigned int*>(workspace);
+  float* cscore = reinterpret_cast<float*>(static_cast<char*>(workspace) + hist_bytes(n));
+  uint16_t* clabel = reinterpret_cast<uint16_t*>(static_cast<char*>(workspace) + hist_bytes(n) + score_bytes(n, h, w));
   const int P = (nms_kernel - 1) / 2;
-  if (from_logits) launch_peaks<true>(heatmap, cscore, clabel, n, c, h, w, P, force_generic, st);
-  else             launch_peaks<false>(heatmap, cscore, clabel, n, c, h, w, P, force_generic, st);
+  CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
+  if (from_logits) launch_peaks<true>(heatmap, cscore, clabel, hist, n, c, h, w, P, force_generic, st);
+  else             launch_peaks<false>(heatmap, cscore, clabel, hist, n, c, h, w, P, force_generic, st);
   CNL_CUDA_CHECK(cudaGetLastError());
 
   DecodeParams p;
-  p.cscore = cscore; p.clabel = clabel; p.box = box_offsets; p.reid = reid;
+  p.cscore = cscore; p.clabel = clabel; p.hist = hist; p.box = box_offsets; p.reid = reid;
   p.H = h; p.W = w; p.E = reid_dim; p.k = num_detections;
   p.normalize = normalize_boxes; p.box_log = box_log; p.mult = box_multiplier; p.stride_f = (float)stride;
   p.boxes = boxes; p.scores = scores; p.labels = reinterpret_cast<long long*>(labels);
   p.indices = reinterpret_cast<long long*>(indices); p.emb = embeddings;
   select_gather_kernel<<<n, kSelThreads, 0, st>>>(p);
+  CNL_CUDA_CHECK(cudaGetLastError());
+  return CNL_OK;
+}
+
+int cnl_sigmoid(const float* in, float* out, size_t n, void* stream) {
+  if (!in || !out) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_sigmoid: null pointer argument");
+  if (n == 0) return CNL_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+  sigmoid_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n);
   CNL_CUDA_CHECK(cudaGetLastError());
   return CNL_OK;
 }

@@ -42,6 +42,58 @@ def _check_map(name: str, t: torch.Tensor, ndim: int = 4) -> torch.Tensor:
     return t.contiguous()
 
 
+class DecodeBuffers:
+    """Pre-allocated outputs + workspace for one decode shape (used inside CUDA-graph capture: no allocation per call)."""
+
+    def __init__(self, n: int, h: int, w: int, k: int, reid_dim: int, device: torch.device):
+        lib = _lib.load()
+        self.n, self.h, self.w, self.k, self.e = n, h, w, k, reid_dim
+        with torch.cuda.device(device):
+            self.scores = torch.empty((n, k), dtype=torch.float32, device=device)
+            self.labels = torch.empty((n, k), dtype=torch.int64, device=device)
+            self.indices = torch.empty((n, k), dtype=torch.int64, device=device)
+            self.boxes = torch.empty((n, k, 4), dtype=torch.float32, device=device)
+            self.emb = torch.empty((n, k, reid_dim), dtype=torch.float32, device=device) if reid_dim else None
+            self.ws = torch.empty(lib.cnl_decode_workspace_bytes(n, h, w) + 256, dtype=torch.uint8, device=device)
+            off = (-self.ws.data_ptr()) % 256
+            self.ws = self.ws[off:]
+
+    def as_dict(self) -> Dict[str, torch.Tensor]:
+        out = {"boxes": self.boxes, "scores": self.scores, "labels": self.labels}
+        if self.emb is not None:
+            out["embeddings"] = self.emb
+        return out
+
+
+def decode_into(bufs: DecodeBuffers, heatmap: torch.Tensor, box_offsets: torch.Tensor, reid: Optional[torch.Tensor], *,
+                num_detections: int, nms_kernel: int, normalize_boxes: bool, box_log: bool, box_multiplier: float,
+                stride: int, from_logits: bool) -> int:
+    """Allocation-free decode on the current stream (CUDA-graph capturable).  Returns the number of launches."""
+    lib = _lib.load()
+    n, c, h, w = heatmap.shape
+    if (n, h, w, num_detections) != (bufs.n, bufs.h, bufs.w, bufs.k):
+        raise ValueError("DecodeBuffers were built for another shape")
+    st = lib.cnl_decode_detections(
+        heatmap.data_ptr(), box_offsets.data_ptr(), reid.data_ptr() if reid is not None else None,
+        n, c, h, w, bufs.e if reid is not None else 0, int(bool(from_logits)), int(nms_kernel), int(num_detections),
+        int(bool(normalize_boxes)), int(bool(box_log)), float(box_multiplier), int(stride),
+        bufs.boxes.data_ptr(), bufs.scores.data_ptr(), bufs.labels.data_ptr(), bufs.indices.data_ptr(),
+        bufs.emb.data_ptr() if (bufs.emb is not None and reid is not None) else None,
+        bufs.ws.data_ptr(), bufs.ws.numel(), torch.cuda.current_stream(heatmap.device).cuda_stream)
+    _lib.check(st, "cnl_decode_detections")
+    return 3            # memset + peaks + select
+
+
+def sigmoid(x: torch.Tensor) -> torch.Tensor:
+    """fp32 logistic through the library (reference models/centernet.py:205)."""
+    lib = _lib.load()
+    x = _check_map("heatmap", x, x.dim())
+    out = torch.empty_like(x)
+    st = lib.cnl_sigmoid(x.data_ptr(), out.data_ptr(), x.numel(), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(st, "cnl_sigmoid")
+    return out
+
+
 def decode_detections(heatmap: torch.Tensor, box_offsets: Optional[torch.Tensor], *, num_detections: int = 100,
                       nms_kernel: int = 3, normalize_boxes: bool = False, box_log: bool = False,
                       box_multiplier: float = 1.0, stride: int = 4, reid: Optional[torch.Tensor] = None,
@@ -65,6 +117,8 @@ def decode_detections(heatmap: torch.Tensor, box_offsets: Optional[torch.Tensor]
             raise ValueError(f"reid must be (N,E,{h},{w}), got {tuple(reid.shape)}")
         e = reid.shape[1]
     k = int(num_detections)
+    if not 1 <= k <= h * w:
+        raise ValueError(f"num_detections={k} must be in 1..H*W={h * w} (torch.topk raises in the reference)")
     with torch.cuda.device(dev):
         scores = torch.empty((n, k), dtype=torch.float32, device=dev)
         labels = torch.empty((n, k), dtype=torch.int64, device=dev)

@@ -1,0 +1,320 @@
+"""Drop-in model object: the reference's Python surface over the sm_100a engine.
+
+G2 surface (authoritative semantics; reference centernet_lightning/models/centernet.py:68-121, 229-304 and
+models/meta.py:41-47, 96):
+    CenterNet(num_classes, backbone, pretrained_backbone, neck, neck_config, head_config, box_log, box_multiplier,
+              heatmap_prior, nms_kernel, num_detections, ...)
+    .model(images) -> {"heatmap": logits, "box_2d": ltrb[, "reid": emb]}      (GenericModel.forward)
+    .decode_detections(heatmap_prob, box_offsets, normalize_boxes=False) -> {"boxes","scores","labels"}
+    .get_topk_from_heatmap(heatmap, pseudo_nms=True) -> (scores, indices, labels)
+    CenterNet.gather_and_decode_boxes(box_offsets, indices, ...)               (staticmethod)
+    .stride, .num_classes, .hparams
+G1 aliases (README.md:27-101, tests/test_models.py:61-99, models/fairmot.py:138-151, utils/image_annotate.py:220-223):
+    forward(images) -> (heatmap_sigmoid, box_2d[, reid]), get_encoded_outputs / get_output_dict, gather_detection2d,
+    gather_tracking2d, inference_detection(img_dir), output_stride.
+Plus the fused entry point this package adds: detect(images) = forward + sigmoid + NMS + top-k + gather in one
+CUDA-graph replay (what reference validation_step :202-205 does in ~70 eager kernels).
+
+State-dict keys are the G2 ones: model.backbone.*, model.neck.*, model.heads.<head>.block_<i>.{conv,bn}.*,
+model.heads.<head>.out_conv.{weight,bias} (reference models/meta.py:26-28, 36-38, 92-95).  The nn.Conv2d /
+nn.BatchNorm2d objects below only HOLD parameters (default torch init, load_state_dict); they are never called.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import namedtuple
+from types import SimpleNamespace
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import decode as _decode
+from . import _lib
+from .engine import Engine, PRECISION_FAST, PRECISION_SPLIT
+from .plan import RESNET_DEPTHS, RESNET_WIDTHS, build_plan
+
+_PRECISIONS = {"split": PRECISION_SPLIT, "fp32": PRECISION_SPLIT, "fast": PRECISION_FAST, "fp16": PRECISION_FAST}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers (same module tree / key names as the reference graph)
+# ----------------------------------------------------------------------------------------------------------------
+class _ConvBn(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3, padding=1, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+
+class _Block(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+
+class _Backbone(nn.Module):
+    stride = 32
+
+    def __init__(self, name):
+        super().__init__()
+        if name not in RESNET_DEPTHS:
+            raise ValueError(f"backbone {name!r}: the sm_100a engine implements {sorted(RESNET_DEPTHS)}")
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        cin = 64
+        for i, (w, d) in enumerate(zip(RESNET_WIDTHS, RESNET_DEPTHS[name])):
+            blocks = []
+            for j in range(d):
+                blocks.append(_Block(cin, w, 2 if (j == 0 and i > 0) else 1))
+                cin = w
+            setattr(self, f"layer{i + 1}", nn.Sequential(*blocks))
+
+    def get_out_channels(self):
+        return list(RESNET_WIDTHS)
+
+
+class _FPN(nn.Module):
+    def __init__(self, in_channels, out_channels=256, fuse_fn="sum"):
+        super().__init__()
+        if fuse_fn != "sum":
+            raise ValueError("the sm_100a engine implements fuse_fn='sum' (reference configs/centernet.yaml:9)")
+        self.stride = 2 ** (len(in_channels) - 1)
+        self.out_channels = out_channels
+        self.lateral = nn.ModuleList([nn.Conv2d(c, out_channels, 1) for c in in_channels])
+        self.output = nn.ModuleList([_ConvBn(out_channels, out_channels) for _ in in_channels[:-1]])
+
+    def get_out_channels(self):
+        return self.out_channels
+
+
+class _Head(nn.Module):
+    def __init__(self, cin, cout, width=256, depth=3, init_bias=None):
+        super().__init__()
+        for i in range(depth):
+            self.add_module(f"block_{i + 1}", _ConvBn(cin if i == 0 else width, width))
+        self.out_conv = nn.Conv2d(width, cout, 1)
+        if init_bias is not None:
+            self.out_conv.bias.data.fill_(init_bias)          # reference models/meta.py:29-30
+        self.depth = depth
+
+
+class EngineModel(nn.Module):
+    """Stands where the reference's GenericModel stands (``CenterNet.model``): same parameters, same call contract
+    ``model(images) -> Dict[str, Tensor]`` of raw head outputs, executed by the sm_100a engine."""
+
+    def __init__(self, backbone: _Backbone, neck: _FPN, heads: nn.Module, precision: int):
+        super().__init__()
+        self.backbone, self.neck, self.heads = backbone, neck, heads
+        self.precision = precision
+        self._engines: Dict[Tuple, Engine] = {}
+        self._register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
+
+    def invalidate(self) -> None:
+        """Drop packed weights / plans (call after changing parameters in place)."""
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()
+
+    def head_names(self) -> List[str]:
+        return [n for n, _ in self.heads.named_children()]
+
+    def engine_for(self, images: torch.Tensor) -> Engine:
+        n, c, h, w = images.shape
+        key = (n, h, w, images.device.index, self.precision)
+        eng = self._engines.get(key)
+        if eng is None:
+            names = self.head_names()
+            depth = getattr(self.heads, names[0]).depth
+            plan = build_plan(self.state_dict(), head_names=names, head_depth=depth)
+            eng = Engine(plan, n, h, w, images.device, precision=self.precision)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError(f"images must be (N,3,H,W), got {tuple(images.shape)}")
+        if not images.is_cuda:
+            raise RuntimeError("images are on the CPU: the cnl_b200 forward runs on CUDA (sm_100a) only, there is no fallback")
+        images = images.float().contiguous()
+        out = self.engine_for(images).forward(images)
+        return {k: v for k, v in out.items()}
+
+
+_Det = namedtuple("EncodedOutputs", ["heatmap", "box_2d"])
+_Trk = namedtuple("EncodedOutputs", ["heatmap", "box_2d", "reid"])
+
+
+class CenterNet(nn.Module):
+    def __init__(self, num_classes: int, backbone: str = "resnet34", pretrained_backbone: bool = False, neck: str = "FPN",
+                 neck_config: Optional[Dict[str, Any]] = None, head_config: Optional[Dict[str, Any]] = None,
+                 box_init_bias: Optional[float] = None, box_log: bool = False, box_multiplier: float = 1.0,
+                 heatmap_prior: float = 0.01, nms_kernel: int = 3, num_detections: int = 100,
+                 reid_dim: int = 0, precision: str = "split", **training_only: Any):
+        super().__init__()
+        if pretrained_backbone:
+            raise RuntimeError("pretrained_backbone=True needs a download; load weights with load_state_dict() instead")
+        if neck != "FPN":
+            raise ValueError(f"neck {neck!r}: the sm_100a engine lowers the FPN neck (SURVEY 8a F2)")
+        if nms_kernel % 2 != 1:
+            raise ValueError("nms_kernel must be odd")
+        neck_config = dict(neck_config or {})
+        head_config = dict(head_config or {})
+        self.hparams = SimpleNamespace(num_classes=num_classes, backbone=backbone, neck=neck, neck_config=neck_config,
+                                       head_config=head_config, box_log=box_log, box_multiplier=box_multiplier,
+                                       heatmap_prior=heatmap_prior, nms_kernel=nms_kernel, num_detections=num_detections,
+                                       reid_dim=reid_dim, precision=precision, **training_only)
+        bb = _Backbone(backbone)
+        nk = _FPN(bb.get_out_channels(), **neck_config)
+        heads = nn.Module()
+        c = nk.get_out_channels()
+        heads.add_module("heatmap", _Head(c, num_classes, init_bias=math.log(heatmap_prior / (1 - heatmap_prior)), **head_config))
+        heads.add_module("box_2d", _Head(c, 4, init_bias=box_init_bias, **head_config))
+        if reid_dim:
+            heads.add_module("reid", _Head(c, reid_dim, **head_config))
+        self.model = EngineModel(bb, nk, heads, _PRECISIONS[precision])
+        self.stride = bb.stride // nk.stride                                   # reference models/meta.py:96
+        self.num_classes = num_classes
+        self._graphs: Dict[Tuple, Any] = {}
+        self.eval()
+
+    # ---- G1 names -------------------------------------------------------------------------------------------
+    @property
+    def output_stride(self) -> int:
+        return self.stride
+
+    def get_encoded_outputs(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return self.model(images)
+
+    get_output_dict = get_encoded_outputs
+
+    def forward(self, images: torch.Tensor):
+        """G1 contract: (sigmoid(heatmap), box_2d[, reid])  (reference tests/test_models.py:88-99, models/tracker.py:100)."""
+        out = self.model(images)
+        heat = _decode.sigmoid(out["heatmap"])
+        if "reid" in out:
+            return _Trk(heat, out["box_2d"], out["reid"])
+        return _Det(heat, out["box_2d"])
+
+    # ---- decode (reference models/centernet.py:229-304) ----------------------------------------------------
+    def decode_detections(self, heatmap: torch.Tensor, box_offsets: torch.Tensor, normalize_boxes: bool = False,
+                          from_logits: bool = False) -> Dict[str, torch.Tensor]:
+        hp = self.hparams
+        out = _decode.decode_detections(heatmap, box_offsets, num_detections=hp.num_detections, nms_kernel=hp.nms_kernel,
+                                        normalize_boxes=normalize_boxes, box_log=hp.box_log,
+                                        box_multiplier=hp.box_multiplier, stride=self.stride, from_logits=from_logits)
+        return {"boxes": out["boxes"], "scores": out["scores"], "labels": out["labels"]}
+
+    def get_topk_from_heatmap(self, heatmap: torch.Tensor, pseudo_nms: bool = True):
+        return _decode.get_topk_from_heatmap(heatmap, self.hparams.num_detections, self.hparams.nms_kernel, pseudo_nms)
+
+    gather_and_decode_boxes = staticmethod(_decode.gather_and_decode_boxes)
+
+    def gather_detection2d(self, heatmap, box_2d=None, num_detections: Optional[int] = None, nms_kernel: Optional[int] = None,
+                           normalize_bbox: bool = False) -> Dict[str, torch.Tensor]:
+        """G1 decode: probabilities + ltrb map (or the tuple/dict forward() returned) -> {"bboxes","labels","scores"}."""
+        heatmap, box_2d, _ = _unpack(heatmap, box_2d, None)
+        hp = self.hparams
+        out = _decode.decode_detections(heatmap, box_2d, num_detections=num_detections or hp.num_detections,
+                                        nms_kernel=nms_kernel or hp.nms_kernel, normalize_boxes=normalize_bbox,
+                                        box_log=hp.box_log, box_multiplier=hp.box_multiplier, stride=self.stride)
+        return {"bboxes": out["boxes"], "labels": out["labels"], "scores": out["scores"]}
+
+    def gather_tracking2d(self, heatmap, box_2d=None, reid=None, num_detections: int = 100, nms_kernel: int = 3,
+                          normalize_bbox: bool = False) -> Dict[str, torch.Tensor]:
+        """reference models/fairmot.py:138-151: + "embeddings" (N,k,E)."""
+        heatmap, box_2d, reid = _unpack(heatmap, box_2d, reid)
+        hp = self.hparams
+        out = _decode.decode_detections(heatmap, box_2d, reid=reid, num_detections=num_detections, nms_kernel=nms_kernel,
+                                        normalize_boxes=normalize_bbox, box_log=hp.box_log,
+                                        box_multiplier=hp.box_multiplier, stride=self.stride)
+        return {"bboxes": out["boxes"], "labels": out["labels"], "scores": out["scores"], "embeddings": out["embeddings"]}
+
+    # ---- fused forward + decode ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def detect(self, images: torch.Tensor, normalize_boxes: bool = False, use_graph: bool = True) -> Dict[str, torch.Tensor]:
+        """images (N,3,H,W) float32 on the GPU -> {"boxes","scores","labels"[, "embeddings"]}: what the reference's
+        validation_step computes at models/centernet.py:204-205, as one CUDA-graph replay of this package's kernels.
+        Returned tensors are static buffers overwritten by the next call with the same shape."""
+        if not images.is_cuda:
+            raise RuntimeError("images are on the CPU: copy them to the GPU first (no CPU fallback)")
+        images = images.float().contiguous()
+        key = (tuple(images.shape), images.device.index, bool(normalize_boxes), self.model.precision)
+        g = self._graphs.get(key)
+        if g is None:
+            g = _DetectGraph(self, images, normalize_boxes, use_graph)
+            self._graphs[key] = g
+        return g.run(images)
+
+    def invalidate(self) -> None:
+        self._graphs.clear()
+        self.model.invalidate()
+
+    # ---- folder inference (reference README.md:49-65) ------------------------------------------------------
+    @torch.no_grad()
+    def inference_detection(self, img_dir: str, img_names: Optional[Sequence[str]] = None, batch_size: int = 4,
+                            num_detections: Optional[int] = None, img_size: int = 512, device: str = "cuda:0"):
+        from .inference import run_folder
+        return run_folder(self, img_dir, img_names, batch_size, num_detections, img_size, torch.device(device))
+
+
+def _unpack(heatmap, box_2d, reid):
+    if isinstance(heatmap, dict):
+        return heatmap["heatmap"], heatmap["box_2d"], heatmap.get("reid", reid)
+    if isinstance(heatmap, (tuple, list)):
+        t = tuple(heatmap)
+        return t[0], t[1], (t[2] if len(t) > 2 else reid)
+    return heatmap, box_2d, reid
+
+
+class _DetectGraph:
+    """forward + decode for one input shape, captured once into a CUDA graph with static in/out buffers."""
+
+    def __init__(self, net: CenterNet, example: torch.Tensor, normalize_boxes: bool, use_graph: bool):
+        self.net = net
+        dev = example.device
+        hp = net.hparams
+        self.engine = net.model.engine_for(example)
+        n = example.shape[0]
+        h, w = example.shape[2] // net.stride, example.shape[3] // net.stride
+        k = hp.num_detections
+        self.static_in = torch.empty_like(example)
+        outs = self.engine.outputs
+        reid = outs.get("reid")
+        self.bufs = _decode.DecodeBuffers(n, h, w, k, reid.shape[1] if reid is not None else 0, dev)
+        self.kw = dict(num_detections=k, nms_kernel=hp.nms_kernel, normalize_boxes=normalize_boxes, box_log=hp.box_log,
+                       box_multiplier=hp.box_multiplier, stride=net.stride, from_logits=True)
+        self.launches = 0
+        self.graph = None
+        self.static_in.copy_(example)
+        self._body()                                        # warm-up (also sets function attributes)
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+
+    def _body(self):
+        outs = self.engine.forward(self.static_in)
+        self.launches = self.engine.last_launches + _decode.decode_into(self.bufs, outs["heatmap"], outs["box_2d"],
+                                                                         outs.get("reid"), **self.kw)
+
+    def run(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self.static_in.copy_(images, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.bufs.as_dict()

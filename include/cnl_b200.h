@@ -67,6 +67,10 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
                           float* embeddings,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Elementwise fp32 logistic 1/(1+exp(-x)) - the `.sigmoid()` the reference applies to the heatmap head
+ * (centernet_lightning/models/centernet.py:205; G1 forward(), tests/test_models.py:88-99). */
+int cnl_sigmoid(const float* in, float* out, size_t n, void* stream);
+
 /* Stand-alone box gather for caller-supplied indices: CenterNet.gather_and_decode_boxes
  * (centernet_lightning/models/centernet.py:263-304, a staticmethod the reference also calls from its
  * loss, :162-165).  indices (N,k) int64 device; boxes (N,k,4) f32, 16-byte aligned.  Out-of-range

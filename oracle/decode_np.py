@@ -44,6 +44,16 @@ def _maxpool_same(h: np.ndarray, k: int) -> np.ndarray:
     return out
 
 
+def candidate_map(heatmap: np.ndarray, nms_kernel: int = 3, pseudo_nms: bool = True):
+    """centernet.py:250-254: per-pixel (best score, label) after pseudo-NMS and the max over classes."""
+    h = np.asarray(heatmap, dtype=np.float32)
+    if pseudo_nms:
+        h = h * (_maxpool_same(h, nms_kernel) == h).astype(np.float32)
+    labels = np.argmax(h, axis=1)
+    best = np.take_along_axis(h, labels[:, None], axis=1)[:, 0]
+    return best, labels
+
+
 def topk_from_heatmap(heatmap: np.ndarray, num_detections: int = 100, nms_kernel: int = 3,
                       pseudo_nms: bool = True):
     """centernet.py:243-261.  heatmap (N,C,H,W) float32 probabilities.

