@@ -65,7 +65,11 @@ struct ConvParams {
 // ------------------------------------------------------------------------------------------------------------
 // The implicit-GEMM convolution kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int NPLANE>
+// CORR = true (CNL_PRECISION_SPLIT): the hi*lo and lo*hi correction products accumulate in their own TMEM accumulator
+// (columns 256..511) and are added to the hi*hi sum in the epilogue.  The tensor core truncates (RZ) after every
+// accumulate step, which biases long sums; keeping the 2^-11-times-smaller correction stream out of the main
+// accumulator cuts the number of roundings at full magnitude by 3x.  It costs the accumulator double buffering.
+template <int NPLANE, bool CORR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap w_map,
                const __grid_constant__ CUtensorMap dst_map, const ConvParams p) {
@@ -145,11 +149,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       uint32_t phase = 0;
       int acc_it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
-        const int as = acc_it & 1;
-        const uint32_t aphase = (acc_it >> 1) & 1;
+        const int as = CORR ? 0 : (acc_it & 1);
+        const uint32_t aphase = CORR ? (acc_it & 1) : ((acc_it >> 1) & 1);
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
+        const uint32_t d_corr = CORR ? (tmem_base + 256) : d_tmem;
         for (int it = 0; it < k_iters; ++it) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -164,8 +169,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             if (NPLANE == 2) {
               const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + kATileBytes);
               const uint64_t b_lo = ptx::make_sw128_kmajor_desc(b_addr + b_tile_bytes);
-              ptx::umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
-              ptx::umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+              ptx::umma_f16(d_corr, a_hi + koff, b_lo + koff, idesc, CORR ? (uint32_t)((it | k) != 0) : 1u);
+              ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);          // smem stage reusable once these MMAs retire
@@ -181,8 +186,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     uint8_t* my_stage = staging + (size_t)(warp - 2) * NPLANE * kStageWarpBytes;
     int acc_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
-      const int as = acc_it & 1;
-      const uint32_t aphase = (acc_it >> 1) & 1;
+      const int as = CORR ? 0 : (acc_it & 1);
+      const uint32_t aphase = CORR ? (acc_it & 1) : ((acc_it >> 1) & 1);
       const int n_idx = tile % p.n_tiles;
       int m_idx = tile / p.n_tiles;
       const int img = m_idx / (p.tiles_h * p.tiles_w);
@@ -201,27 +206,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const __half* res_px = nullptr;
         if (p.res != nullptr && valid)
           res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
-        for (int c64 = 0; c64 < p.n_tile / 64; ++c64) {
-          uint32_t r[64];
-          ptx::tmem_ld_32x32b_x32(taddr + c64 * 64, r);
-          ptx::tmem_ld_32x32b_x32(taddr + c64 * 64 + 32, r + 32);
-          ptx::tmem_ld_wait();
-          const int cb = n_idx * p.n_tile + c64 * 64;
-          float v[64];
+        for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c32 * 32, r);
+          if (CORR) {
+            uint32_t rc[32];
+            ptx::tmem_ld_32x32b_x32(taddr + 256 + c32 * 32, rc);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 64; j += 4) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+          } else {
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          const int cb = n_idx * p.n_tile + c32 * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
-            v[j + 0] = fmaf(__uint_as_float(r[j + 0]), p.wscale_inv, b4.x);
-            v[j + 1] = fmaf(__uint_as_float(r[j + 1]), p.wscale_inv, b4.y);
-            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), p.wscale_inv, b4.z);
-            v[j + 3] = fmaf(__uint_as_float(r[j + 3]), p.wscale_inv, b4.w);
+            v[j + 0] = fmaf(v[j + 0], p.wscale_inv, b4.x);
+            v[j + 1] = fmaf(v[j + 1], p.wscale_inv, b4.y);
+            v[j + 2] = fmaf(v[j + 2], p.wscale_inv, b4.z);
+            v[j + 3] = fmaf(v[j + 3], p.wscale_inv, b4.w);
           }
           if (res_px != nullptr) {
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl) {
               const uint4* rp = reinterpret_cast<const uint4*>(res_px + pl * p.res_plane_elems + cb);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 const uint4 u = __ldg(rp + j);
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -235,13 +249,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
-          // previous TMA store out of this warp's staging buffers must have finished reading them
-          if (lane == 0) ptx::tma_store_wait_read<0>();
-          __syncwarp();
+          if ((c32 & 1) == 0) {
+            // the previous TMA store out of this warp's staging buffers must have finished reading them
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {                  // 8 channels = one 16-byte chunk, XOR-swizzled by row
+          for (int j = 0; j < 4; ++j) {                  // 8 channels = one 16-byte chunk, XOR-swizzled by row
             uint4 hi, lo;
             __half2* hh = reinterpret_cast<__half2*>(&hi);
             __half2* ll = reinterpret_cast<__half2*>(&lo);
@@ -255,31 +271,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 ll[t] = __floats2half2_rn(a - back.x, b - back.y);
               }
             }
-            const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
+            const int chunk = (c32 & 1) * 4 + j;
+            const int off = lane * 128 + ((chunk ^ (lane & 7)) << 4);
             *reinterpret_cast<uint4*>(my_stage + off) = hi;
             if (NPLANE == 2) *reinterpret_cast<uint4*>(my_stage + kStageWarpBytes + off) = lo;
           }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
+          if (c32 & 1) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
+              const int c64 = n_idx * p.n_tile + (c32 >> 1) * 64;
 #pragma unroll
-            for (int pl = 0; pl < NPLANE; ++pl)
-              ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + cb, wq, hq, img + pl * p.n_img);
-            ptx::tma_store_commit();
+              for (int pl = 0; pl < NPLANE; ++pl)
+                ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + c64, wq, hq, img + pl * p.n_img);
+              ptx::tma_store_commit();
+            }
           }
         }
       } else {
         for (int c16 = 0; c16 < p.n_tile / 16; ++c16) {
           uint32_t r[16];
+          float v[16];
           ptx::tmem_ld_32x32b_x16(taddr + c16 * 16, r);
-          ptx::tmem_ld_wait();
+          if (CORR) {
+            uint32_t rc[16];
+            ptx::tmem_ld_32x32b_x16(taddr + 256 + c16 * 16, rc);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+          } else {
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
           const int cb = n_idx * p.n_tile + c16 * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c = cb + j;
             if (valid && c < p.cout_real) {
-              float val = fmaf(__uint_as_float(r[j]), p.wscale_inv, __ldg(p.bias + c));
+              float val = fmaf(v[j], p.wscale_inv, __ldg(p.bias + c));
               if (p.relu) val = fmaxf(val, 0.0f);
               p.out_nchw[(((long long)img * p.cout_real + c) * p.out_h + h) * p.out_w + w] = val;
             }
@@ -307,14 +338,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kStemTile = 16;                                  // 16x16 conv outputs per CTA
 constexpr int kStemPatch = kStemTile * 2 + 5;                  // 37 input rows/cols
-constexpr int kStemSmemBytes = (3 * kStemPatch * kStemPatch + 147 * 64) * 4;
+constexpr int kStemInFloats = (3 * kStemPatch * kStemPatch + 3) & ~3;   // keep the weight block 16-byte aligned
+constexpr int kStemSmemBytes = (kStemInFloats + 147 * 64) * 4;
 
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ image, const float* __restrict__ wk /*[147][64]*/, const float* __restrict__ bias,
                  float* __restrict__ out /*[N][H/2][W/2][64] fp32*/, int H, int W) {
-  extern __shared__ float s_mem[];
+  extern __shared__ __align__(16) float s_mem[];
   float* s_in = s_mem;                                         // [3][37][37]
-  float* s_w = s_mem + 3 * kStemPatch * kStemPatch;            // [147][64]
+  float* s_w = s_mem + kStemInFloats;                          // [147][64]
   const int OH = H / 2, OW = W / 2;
   const int n = blockIdx.z;
   const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
@@ -590,10 +622,10 @@ int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_bu
   if (!out || !buffers || !ops || n_buffers < 2 || n_ops < 1) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: bad arguments");
   if (batch < 1 || height < 32 || width < 32 || height % 32 || width % 32)
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: input must be a multiple of 32 in both dimensions (got %dx%d)", height, width);
-  if (precision != CNL_PRECISION_SPLIT && precision != CNL_PRECISION_FAST) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: precision");
+  if (precision != CNL_PRECISION_SPLIT && precision != CNL_PRECISION_FAST && precision != CNL_PRECISION_SPLIT_FUSED) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_create: precision");
   cnl_engine* e = new cnl_engine();
   e->batch = batch; e->height = height; e->width = width; e->precision = precision; e->device = device;
-  e->planes = (precision == CNL_PRECISION_SPLIT) ? 2 : 1;
+  e->planes = (precision == CNL_PRECISION_FAST) ? 1 : 2;
   e->uploaded_arena = nullptr;
   e->num_sms = 148;
   size_t off = 0;
@@ -652,8 +684,9 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
   CNL_CUDA_CHECK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, e->device));
   if (cc_major != 10) return fail(CNL_ERR_UNSUPPORTED, "cnl_b200 kernels are built for sm_100a only (device has compute capability %d.x)", cc_major);
   e->num_sms = dev_sms;
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CNL_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
   uint8_t* base = static_cast<uint8_t*>(arena);
   const int planes = e->planes;
@@ -753,8 +786,9 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h;
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = std::min(total_tiles, e->num_sms);
-    if (planes == 2) conv_tc_kernel<2><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
-    else             conv_tc_kernel<1><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+    if (e->precision == CNL_PRECISION_SPLIT)            conv_tc_kernel<2, true><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) conv_tc_kernel<2, false><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+    else                                                conv_tc_kernel<1, false><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
     ++n_launch;
     CNL_CUDA_CHECK(cudaGetLastError());
     (void)src;

@@ -35,7 +35,7 @@ from . import _lib
 from .engine import Engine, PRECISION_FAST, PRECISION_SPLIT
 from .plan import RESNET_DEPTHS, RESNET_WIDTHS, build_plan
 
-_PRECISIONS = {"split": PRECISION_SPLIT, "fp32": PRECISION_SPLIT, "fast": PRECISION_FAST, "fp16": PRECISION_FAST}
+_PRECISIONS = {"split": PRECISION_SPLIT, "fp32": PRECISION_SPLIT, "split_fused": 2, "fast": PRECISION_FAST, "fp16": PRECISION_FAST}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -114,7 +114,7 @@ class EngineModel(nn.Module):
         self.backbone, self.neck, self.heads = backbone, neck, heads
         self.precision = precision
         self._engines: Dict[Tuple, Engine] = {}
-        self._register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
 
     def invalidate(self) -> None:
         """Drop packed weights / plans (call after changing parameters in place)."""
@@ -255,6 +255,28 @@ class CenterNet(nn.Module):
     def invalidate(self) -> None:
         self._graphs.clear()
         self.model.invalidate()
+
+    @torch.no_grad()
+    def init_synthetic_(self, seed: int = 0) -> "CenterNet":
+        """Deterministic random weights with healthy activation statistics (no network access for checkpoints):
+        He-normal convs, BN gamma ~ U(0.5,1.5) (residual-branch bn2 damped), beta ~ N(0,0.1), unit running variance.
+        Dense throughput does not depend on the values, but dead (all-zero) activations would flatter power/clocks."""
+        g = torch.Generator().manual_seed(seed)
+        for name, mod in self.model.named_modules():
+            if isinstance(mod, nn.Conv2d):
+                fan_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1]
+                mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
+                if mod.bias is not None and not name.endswith("heatmap.out_conv"):
+                    mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+            elif isinstance(mod, nn.BatchNorm2d):
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+                if name.endswith("bn2"):
+                    mod.weight.mul_(0.3)
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+                mod.running_mean.zero_()
+                mod.running_var.fill_(1.0)
+        self.invalidate()
+        return self
 
     # ---- folder inference (reference README.md:49-65) ------------------------------------------------------
     @torch.no_grad()

@@ -91,12 +91,16 @@ int cnl_gather_boxes(const float* box_offsets, const int64_t* indices, int n, in
  * precision: 0 = CNL_PRECISION_SPLIT  activations and weights are carried as fp16 hi+lo pairs and
  *                every product is accumulated in fp32 from three tcgen05 passes (hi*hi, hi*lo, lo*hi):
  *                fp32-equivalent results (the 1e-3 parity bar of BASELINE.json).
+ *                The two correction products accumulate in their own TMEM accumulator (the tensor core truncates
+ *                after every accumulate step; this keeps the main sum to one third of the roundings).
+ *            2 = CNL_PRECISION_SPLIT_FUSED  same three passes into ONE accumulator (double-buffered, slightly
+ *                faster, ~3x the accumulated rounding bias of mode 0).
  *            1 = CNL_PRECISION_FAST   single fp16 pass, fp32 accumulate (reduced precision, reported
  *                separately; does not meet the 1e-3 bar).
  * ------------------------------------------------------------------------------------------ */
 typedef struct cnl_engine cnl_engine;
 
-enum { CNL_PRECISION_SPLIT = 0, CNL_PRECISION_FAST = 1 };
+enum { CNL_PRECISION_SPLIT = 0, CNL_PRECISION_FAST = 1, CNL_PRECISION_SPLIT_FUSED = 2 };
 
 /* One fused convolution: out = act(conv(in, w) + bias [+ residual]).  Host-side description. */
 typedef struct {
