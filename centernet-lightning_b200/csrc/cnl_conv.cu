@@ -47,7 +47,7 @@ struct ConvParams {
   int n_img, out_h, out_w;
   int tw, th, tiles_w, tiles_h, m_tiles;
   int n_tiles, n_tile;
-  int ksize, stride, pad, kblocks;
+  int kh, kw, stride, pad_h, pad_w, kblocks;
   int src_c_off, dst_c_off;
   int relu;
   int out_mode;                 // 0 = NHWC fp16 planes via TMA store, 1 = NCHW fp32 direct stores
@@ -87,7 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   const int b_tile_bytes = p.n_tile * kBlockK * 2;
   const int stage_bytes = NPLANE * (kATileBytes + b_tile_bytes);
   uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;        // [4 warps][NPLANE][4096], 1024-aligned
-  const int taps = p.ksize * p.ksize;
+  const int taps = p.kh * p.kw;
   const int k_iters = taps * p.kblocks;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -121,9 +121,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         const int h0 = (m_idx / p.tiles_w) * p.th;
         const int w0 = (m_idx % p.tiles_w) * p.tw;
         for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.ksize, s = tap - r * p.ksize;
-          const int cw = w0 * p.stride + s - p.pad;
-          const int ch = h0 * p.stride + r - p.pad;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          const int cw = w0 * p.stride + s - p.pad_w;
+          const int ch = h0 * p.stride + r - p.pad_h;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
@@ -334,69 +334,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Stem: conv7x7/2 (3->64) + bias + ReLU on CUDA cores (Cin = 3 has no tensor-core shape), then 3x3/2 max-pool.
+// Stem: conv7x7/2 (3->64) + BN + ReLU + max-pool3x3/2 on the tensor cores.
+//   Cin = 3 has no UMMA shape, so the image is first rewritten as an "im2row" tensor T at half resolution:
+//   space-to-depth by 2 turns the 7x7/2 conv into a 4x4/1 conv over 12 channels (3 colours x 2x2 phases); the four
+//   horizontal taps are unrolled into the channel dimension (4 x 12 = 48, zero-padded to 64 = one 128-byte swizzle
+//   row).  What is left is a conv with 4 VERTICAL taps, Cin = 64, Cout = 64, which the generic tcgen05 kernel above
+//   runs as kh=4, kw=1 (vertical taps are plain TMA row offsets; rows outside the image are zero-filled = padding).
+//   A plane-aware 3x3/2 max-pool finishes the stem.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kStemTile = 16;                                  // 16x16 conv outputs per CTA
-constexpr int kStemPatch = kStemTile * 2 + 5;                  // 37 input rows/cols
-constexpr int kStemInFloats = (3 * kStemPatch * kStemPatch + 3) & ~3;   // keep the weight block 16-byte aligned
-constexpr int kStemSmemBytes = (kStemInFloats + 147 * 64) * 4;
-
+// T[n][sy][sx][dxi*12 + c*4 + py*2 + px] = image[n][c][2*sy + py][2*(sx + dxi - 2) + px]   (0 outside the image)
+template <int NPLANE>
 __global__ void __launch_bounds__(256)
-stem_conv_kernel(const float* __restrict__ image, const float* __restrict__ wk /*[147][64]*/, const float* __restrict__ bias,
-                 float* __restrict__ out /*[N][H/2][W/2][64] fp32*/, int H, int W) {
-  extern __shared__ __align__(16) float s_mem[];
-  float* s_in = s_mem;                                         // [3][37][37]
-  float* s_w = s_mem + kStemInFloats;                          // [147][64]
-  const int OH = H / 2, OW = W / 2;
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
-  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-  for (int i = threadIdx.x; i < 147 * 64; i += 256) s_w[i] = wk[i];
-  for (int i = threadIdx.x; i < 3 * kStemPatch * kStemPatch; i += 256) {
-    int c = i / (kStemPatch * kStemPatch);
-    int rem = i - c * kStemPatch * kStemPatch;
-    int y = iy0 + rem / kStemPatch, x = ix0 + rem % kStemPatch;
-    s_in[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(image + (((size_t)n * 3 + c) * H + y) * W + x) : 0.0f;
-  }
-  __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc[64];
+stem_im2row_kernel(const float* __restrict__ image, __half* __restrict__ T, int N, int H, int W, long long plane_elems) {
+  const int SH = H / 2, SW = W / 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * SH * SW) return;
+  const int sx = (int)(t % SW);
+  const int sy = (int)((t / SW) % SH);
+  const int n = (int)(t / ((long long)SW * SH));
+  float v[64];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
+  for (int j = 48; j < 64; ++j) v[j] = 0.0f;
+#pragma unroll
   for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 7; ++r) {
-      const float* in_row = s_in + (c * kStemPatch + 2 * ty + r) * kStemPatch + 2 * tx;
-      const float* w_row = s_w + ((c * 7 + r) * 7) * 64;
 #pragma unroll
-      for (int s = 0; s < 7; ++s) {
-        const float x = in_row[s];
-        const float4* w4 = reinterpret_cast<const float4*>(w_row + s * 64);
+    for (int py = 0; py < 2; ++py) {
+      const float* row = image + (((size_t)n * 3 + c) * H + (2 * sy + py)) * W;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 wv = w4[j];
-          acc[4 * j + 0] = fmaf(x, wv.x, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(x, wv.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(x, wv.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(x, wv.w, acc[4 * j + 3]);
-        }
+      for (int dxi = 0; dxi < 4; ++dxi) {
+        const int xs = sx + dxi - 2;
+        float2 f = make_float2(0.0f, 0.0f);
+        if (xs >= 0 && xs < SW) f = __ldg(reinterpret_cast<const float2*>(row + 2 * xs));
+        v[dxi * 12 + c * 4 + py * 2 + 0] = f.x;
+        v[dxi * 12 + c * 4 + py * 2 + 1] = f.y;
       }
     }
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy < OH && ox < OW) {
-    float4* o4 = reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox) * 64);
+  __half* o = T + (size_t)t * 64;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j);
-      o4[j] = make_float4(fmaxf(acc[4 * j] + b.x, 0.f), fmaxf(acc[4 * j + 1] + b.y, 0.f), fmaxf(acc[4 * j + 2] + b.z, 0.f),
-                          fmaxf(acc[4 * j + 3] + b.w, 0.f));
+  for (int j = 0; j < 8; ++j) {
+    uint4 hi, lo;
+    __half2* hh = reinterpret_cast<__half2*>(&hi);
+    __half2* ll = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = v[j * 8 + 2 * q], b = v[j * 8 + 2 * q + 1];
+      const __half2 h2 = __floats2half2_rn(a, b);
+      hh[q] = h2;
+      const float2 back = __half22float2(h2);
+      ll[q] = __floats2half2_rn(a - back.x, b - back.y);
     }
+    reinterpret_cast<uint4*>(o)[j] = hi;
+    if (NPLANE == 2) reinterpret_cast<uint4*>(o + plane_elems)[j] = lo;
   }
 }
 
-// 3x3 stride-2 pad-1 max-pool over the fp32 NHWC stem output -> NHWC fp16 planes.  One thread = one pixel x 8 channels.
+// 3x3 stride-2 pad-1 max-pool over NHWC fp16 planes (value = hi + lo).  One thread = one output pixel x 8 channels.
 template <int NPLANE>
-__global__ void stem_pool_kernel(const float* __restrict__ in /*[N][IH][IW][64]*/, __half* __restrict__ out, int N, int IH,
-                                 int IW, long long plane_elems) {
+__global__ void __launch_bounds__(256)
+pool_planes_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int IH, int IW, long long in_plane,
+                   long long out_plane) {
   const int OH = IH / 2, OW = IW / 2;
   const long long total = (long long)N * OH * OW * 8;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,10 +412,20 @@ __global__ void stem_pool_kernel(const float* __restrict__ in /*[N][IH][IW][64]*
     for (int dx = -1; dx <= 1; ++dx) {
       const int x = 2 * ox + dx;
       if (x < 0 || x >= IW) continue;
-      const float4* p4 = reinterpret_cast<const float4*>(in + (((size_t)n * IH + y) * IW + x) * 64 + c8 * 8);
-      const float4 a = __ldg(p4), b = __ldg(p4 + 1);
-      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
-      m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+      const size_t o = (((size_t)n * IH + y) * IW + x) * 64 + c8 * 8;
+      const uint4 uh = __ldg(reinterpret_cast<const uint4*>(in + o));
+      const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+      float f[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 a = __half22float2(hh[q]); f[2 * q] = a.x; f[2 * q + 1] = a.y; }
+      if (NPLANE == 2) {
+        const uint4 ul = __ldg(reinterpret_cast<const uint4*>(in + in_plane + o));
+        const __half2* ll = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 a = __half22float2(ll[q]); f[2 * q] += a.x; f[2 * q + 1] += a.y; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
     }
   }
   uint4 hi, lo;
@@ -434,7 +440,7 @@ __global__ void stem_pool_kernel(const float* __restrict__ in /*[N][IH][IW][64]*
   }
   const size_t o = (((size_t)n * OH + oy) * OW + ox) * 64 + c8 * 8;
   *reinterpret_cast<uint4*>(out + o) = hi;
-  if (NPLANE == 2) *reinterpret_cast<uint4*>(out + plane_elems + o) = lo;
+  if (NPLANE == 2) *reinterpret_cast<uint4*>(out + out_plane + o) = lo;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -488,7 +494,7 @@ struct OpInfo {
   size_t w_offset, bias_offset, scratch_offset;
   std::vector<__half> w_packed;       // [plane][tap][cout_pad][cin]
   std::vector<float> bias_packed;     // [cout_pad]   (stem: [64]);
-  std::vector<float> w_stem;          // stem: [147][64] fp32
+  size_t stem_t_offset, stem_s_offset;   // stem scratch: im2row tensor T and the un-pooled conv output S
   CUtensorMap src_map, w_map, dst_map;
 };
 
@@ -536,6 +542,8 @@ static void split_half(float x, __half* hi, __half* lo) {
   *lo = __float2half_rn(x - __half2float(*hi));
 }
 
+static void pack_split_weights(OpInfo& op, const std::vector<float>& w, int cout, int cin, int taps, int planes);
+
 static int prepare_conv(cnl_engine* e, OpInfo& op) {
   const cnl_conv_desc& d = op.d;
   const BufferInfo& src = e->bufs[d.src];
@@ -576,25 +584,32 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = d.ksize * d.ksize;
-  float wmax = 0.f;
-  const size_t nw = (size_t)d.cout * d.cin * taps;
-  for (size_t i = 0; i < nw; ++i) wmax = std::max(wmax, std::fabs(d.weight_host[i]));
-  int ex = 0;
-  if (wmax > 0.f) { std::frexp(wmax, &ex); }
-  op.wscale = std::ldexp(1.0f, 13 - ex);               // max |w| * wscale in [4096, 8192)
-  op.w_packed.assign((size_t)planes * taps * op.cout_pad * d.cin, __float2half_rn(0.f));
+  std::vector<float> wt((size_t)d.cout * taps * d.cin);
   for (int co = 0; co < d.cout; ++co)
     for (int ci = 0; ci < d.cin; ++ci)
-      for (int t = 0; t < taps; ++t) {
-        const float w = d.weight_host[((size_t)co * d.cin + ci) * taps + t] * op.wscale;
-        __half hi, lo;
-        split_half(w, &hi, &lo);
-        op.w_packed[(((size_t)0 * taps + t) * op.cout_pad + co) * d.cin + ci] = hi;
-        if (planes == 2) op.w_packed[(((size_t)1 * taps + t) * op.cout_pad + co) * d.cin + ci] = lo;
-      }
+      for (int t = 0; t < taps; ++t) wt[((size_t)co * taps + t) * d.cin + ci] = d.weight_host[((size_t)co * d.cin + ci) * taps + t];
+  pack_split_weights(op, wt, d.cout, d.cin, taps, planes);
   op.bias_packed.assign(op.cout_pad, 0.f);
   for (int co = 0; co < d.cout; ++co) op.bias_packed[co] = d.bias_host[co];
   return CNL_OK;
+}
+
+static void pack_split_weights(OpInfo& op, const std::vector<float>& w /*[cout][taps][cin]*/, int cout, int cin, int taps,
+                               int planes) {
+  float wmax = 0.f;
+  for (float x : w) wmax = std::max(wmax, std::fabs(x));
+  int ex = 0;
+  if (wmax > 0.f) std::frexp(wmax, &ex);
+  op.wscale = std::ldexp(1.0f, 13 - ex);               // max |w| * wscale in [4096, 8192)
+  op.w_packed.assign((size_t)planes * taps * op.cout_pad * cin, __float2half_rn(0.f));
+  for (int co = 0; co < cout; ++co)
+    for (int t = 0; t < taps; ++t)
+      for (int ci = 0; ci < cin; ++ci) {
+        __half hi, lo;
+        split_half(w[((size_t)co * taps + t) * cin + ci] * op.wscale, &hi, &lo);
+        op.w_packed[(((size_t)0 * taps + t) * op.cout_pad + co) * cin + ci] = hi;
+        if (planes == 2) op.w_packed[(((size_t)1 * taps + t) * op.cout_pad + co) * cin + ci] = lo;
+      }
 }
 
 static int prepare_stem(cnl_engine* e, OpInfo& op) {
@@ -604,9 +619,35 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   if (!src.fp32_nchw || src.channels != 3 || d.cin != 3 || d.cout != 64 || d.ksize != 7 || d.stride != 2 || d.pad != 3 ||
       dst.fp32_nchw || dst.channels != 64 || dst.h * 4 != src.h || dst.w * 4 != src.w)
     return fail(CNL_ERR_UNSUPPORTED, "stem must be conv7x7/2 (3->64) + max-pool3x3/2 from the fp32 image");
-  op.w_stem.assign(147 * 64, 0.f);
+  // inner conv: 4 vertical taps over the im2row tensor, Cin = 64 (48 used), Cout = 64, at half resolution
+  const int sw = e->width / 2, sh = e->height / 2;
+  op.cout_pad = 64; op.n_tile = 64; op.n_tiles = 1;
+  op.tw = std::max(8, std::min(128, pow2_ceil(sw)));
+  op.th = kBlockM / op.tw;
+  op.tiles_w = (sw + op.tw - 1) / op.tw;
+  op.tiles_h = (sh + op.th - 1) / op.th;
+  op.store_w = std::min(op.tw, 32);
+  op.store_h = 32 / op.store_w;
+  const int planes = e->planes;
+  const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
+  op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - 4 * planes * kStageWarpBytes) / stage_bytes);
+  // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
+  //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
+  std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
   for (int co = 0; co < 64; ++co)
-    for (int k = 0; k < 147; ++k) op.w_stem[(size_t)k * 64 + co] = d.weight_host[(size_t)co * 147 + k];
+    for (int c = 0; c < 3; ++c)
+      for (int dyi = 0; dyi < 4; ++dyi)
+        for (int py = 0; py < 2; ++py) {
+          const int ky = 2 * dyi + py - 1;
+          if (ky < 0 || ky > 6) continue;
+          for (int dxi = 0; dxi < 4; ++dxi)
+            for (int px = 0; px < 2; ++px) {
+              const int kx = 2 * dxi + px - 1;
+              if (kx < 0 || kx > 6) continue;
+              w2[((size_t)co * 4 + dyi) * 64 + dxi * 12 + c * 4 + py * 2 + px] = d.weight_host[(((size_t)co * 3 + c) * 7 + ky) * 7 + kx];
+            }
+        }
+  pack_split_weights(op, w2, 64, 64, 4, planes);
   op.bias_packed.assign(d.bias_host, d.bias_host + 64);
   return CNL_OK;
 }
@@ -650,9 +691,12 @@ int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_bu
     if (st != CNL_OK) { delete e; return st; }
     op.d.weight_host = nullptr; op.d.bias_host = nullptr;
     if (op.d.kind == 1) {
-      op.w_offset = off; off += align_up(op.w_stem.size() * 4, 1024);
+      const size_t half_res = (size_t)batch * (height / 2) * (width / 2) * 64 * 2 * e->planes;
+      op.w_offset = off; off += align_up(op.w_packed.size() * 2, 1024);
       op.bias_offset = off; off += align_up(64 * 4, 1024);
-      op.scratch_offset = off; off += align_up((size_t)batch * (height / 2) * (width / 2) * 64 * 4, 1024);
+      op.stem_t_offset = off; off += align_up(half_res, 1024);
+      op.stem_s_offset = off; off += align_up(half_res, 1024);
+      op.scratch_offset = 0;
     } else {
       op.w_offset = off; off += align_up(op.w_packed.size() * 2, 1024);
       op.bias_offset = off; off += align_up(op.bias_packed.size() * 4, 1024);
@@ -687,14 +731,29 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
   CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
   uint8_t* base = static_cast<uint8_t*>(arena);
   const int planes = e->planes;
   for (OpInfo& op : e->ops) {
     const cnl_conv_desc& d = op.d;
     if (d.kind == 1) {
-      CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_stem.data(), op.w_stem.size() * 4, cudaMemcpyHostToDevice, st));
+      CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_packed.data(), op.w_packed.size() * 2, cudaMemcpyHostToDevice, st));
       CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.bias_offset, op.bias_packed.data(), 64 * 4, cudaMemcpyHostToDevice, st));
+      const cuuint64_t sw = e->width / 2, sh = e->height / 2;
+      cuuint64_t dims[4] = {64, sw, sh, (cuuint64_t)e->batch * planes};
+      cuuint64_t str[3] = {128, sw * 128, sh * sw * 128};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      cuuint32_t box_in[4] = {64, (cuuint32_t)op.tw, (cuuint32_t)op.th, 1};
+      cuuint32_t box_out[4] = {64, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
+      int r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str, box_in, es, "stem im2row");
+      if (r) return r;
+      r = encode_map(&op.dst_map, base + op.stem_s_offset, 4, dims, str, box_out, es, "stem out");
+      if (r) return r;
+      cuuint64_t wd[3] = {64, 64, (cuuint64_t)4 * planes};
+      cuuint64_t ws[2] = {128, 64 * 128};
+      cuuint32_t wb[3] = {64, 64, 1};
+      cuuint32_t we[3] = {1, 1, 1};
+      r = encode_map(&op.w_map, base + op.w_offset, 3, wd, ws, wb, we, "stem weights");
+      if (r) return r;
       continue;
     }
     CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_packed.data(), op.w_packed.size() * 2, cudaMemcpyHostToDevice, st));
@@ -742,56 +801,64 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
   uint8_t* base = static_cast<uint8_t*>(arena);
   const int planes = e->planes;
   int n_launch = 0;
-  for (int i = first_op; i < last_op; ++i) {
-    OpInfo& op = e->ops[i];
-    const cnl_conv_desc& d = op.d;
-    const BufferInfo& src = e->bufs[d.src];
-    const BufferInfo& dst = e->bufs[d.dst];
-    if (d.kind == 1) {
-      if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
-      float* scratch = reinterpret_cast<float*>(base + op.scratch_offset);
-      const int OH = e->height / 2, OW = e->width / 2;
-      dim3 grid((OW + kStemTile - 1) / kStemTile, (OH + kStemTile - 1) / kStemTile, e->batch);
-      stem_conv_kernel<<<grid, 256, kStemSmemBytes, st>>>(image, reinterpret_cast<const float*>(base + op.w_offset),
-                                                          reinterpret_cast<const float*>(base + op.bias_offset), scratch,
-                                                          e->height, e->width);
-      const long long total = (long long)e->batch * (OH / 2) * (OW / 2) * 8;
-      const int blocks = (int)((total + 255) / 256);
-      __half* o = reinterpret_cast<__half*>(base + dst.offset);
-      if (planes == 2) stem_pool_kernel<2><<<blocks, 256, 0, st>>>(scratch, o, e->batch, OH, OW, dst.plane_elems);
-      else             stem_pool_kernel<1><<<blocks, 256, 0, st>>>(scratch, o, e->batch, OH, OW, dst.plane_elems);
-      n_launch += 2;
-      CNL_CUDA_CHECK(cudaGetLastError());
-      continue;
-    }
-    ConvParams p;
-    p.n_img = e->batch; p.out_h = dst.h; p.out_w = dst.w;
-    p.tw = op.tw; p.th = op.th; p.tiles_w = op.tiles_w; p.tiles_h = op.tiles_h;
-    p.m_tiles = e->batch * op.tiles_w * op.tiles_h;
-    p.n_tiles = op.n_tiles; p.n_tile = op.n_tile;
-    p.ksize = d.ksize; p.stride = d.stride; p.pad = d.pad; p.kblocks = d.cin / 64;
-    p.src_c_off = d.src_c_off; p.dst_c_off = d.dst_c_off;
-    p.relu = d.relu;
-    p.out_mode = dst.fp32_nchw ? 1 : 0;
-    p.cout_real = d.cout;
-    p.wscale_inv = 1.0f / op.wscale;
-    p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
-    p.out_nchw = dst.fp32_nchw ? reinterpret_cast<float*>(base + dst.offset) : nullptr;
-    p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
-    if (d.residual >= 0) {
-      const BufferInfo& rb = e->bufs[d.residual];
-      p.res = reinterpret_cast<const __half*>(base + rb.offset);
-      p.res_up = d.residual_up; p.res_c = rb.channels; p.res_h = rb.h; p.res_w = rb.w; p.res_plane_elems = rb.plane_elems;
-    }
-    p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h;
+  auto launch_conv = [&](const ConvParams& p, const OpInfo& op) {
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int grid = std::min(total_tiles, e->num_sms);
     if (e->precision == CNL_PRECISION_SPLIT)            conv_tc_kernel<2, true><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
     else if (e->precision == CNL_PRECISION_SPLIT_FUSED) conv_tc_kernel<2, false><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
     else                                                conv_tc_kernel<1, false><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+  };
+  for (int i = first_op; i < last_op; ++i) {
+    OpInfo& op = e->ops[i];
+    const cnl_conv_desc& d = op.d;
+    const BufferInfo& dst = e->bufs[d.dst];
+    ConvParams p;
+    p.n_img = e->batch;
+    p.tw = op.tw; p.th = op.th; p.tiles_w = op.tiles_w; p.tiles_h = op.tiles_h;
+    p.m_tiles = e->batch * op.tiles_w * op.tiles_h;
+    p.n_tiles = op.n_tiles; p.n_tile = op.n_tile;
+    p.relu = d.relu;
+    p.wscale_inv = 1.0f / op.wscale;
+    p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
+    p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
+    p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h;
+    if (d.kind == 1) {
+      if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
+      const int SH = e->height / 2, SW = e->width / 2;
+      const long long half_plane = (long long)e->batch * SH * SW * 64;
+      __half* T = reinterpret_cast<__half*>(base + op.stem_t_offset);
+      __half* S = reinterpret_cast<__half*>(base + op.stem_s_offset);
+      const long long npix = (long long)e->batch * SH * SW;
+      const int b1 = (int)((npix + 255) / 256);
+      if (planes == 2) stem_im2row_kernel<2><<<b1, 256, 0, st>>>(image, T, e->batch, e->height, e->width, half_plane);
+      else             stem_im2row_kernel<1><<<b1, 256, 0, st>>>(image, T, e->batch, e->height, e->width, half_plane);
+      p.out_h = SH; p.out_w = SW;
+      p.kh = 4; p.kw = 1; p.stride = 1; p.pad_h = 2; p.pad_w = 0; p.kblocks = 1;
+      p.src_c_off = 0; p.dst_c_off = 0; p.out_mode = 0; p.cout_real = 64; p.out_nchw = nullptr;
+      launch_conv(p, op);
+      const long long total = (long long)e->batch * (SH / 2) * (SW / 2) * 8;
+      const int b2 = (int)((total + 255) / 256);
+      __half* o = reinterpret_cast<__half*>(base + dst.offset);
+      if (planes == 2) pool_planes_kernel<2><<<b2, 256, 0, st>>>(S, o, e->batch, SH, SW, half_plane, dst.plane_elems);
+      else             pool_planes_kernel<1><<<b2, 256, 0, st>>>(S, o, e->batch, SH, SW, half_plane, dst.plane_elems);
+      n_launch += 3;
+      CNL_CUDA_CHECK(cudaGetLastError());
+      continue;
+    }
+    p.out_h = dst.h; p.out_w = dst.w;
+    p.kh = d.ksize; p.kw = d.ksize; p.stride = d.stride; p.pad_h = d.pad; p.pad_w = d.pad; p.kblocks = d.cin / 64;
+    p.src_c_off = d.src_c_off; p.dst_c_off = d.dst_c_off;
+    p.out_mode = dst.fp32_nchw ? 1 : 0;
+    p.cout_real = d.cout;
+    p.out_nchw = dst.fp32_nchw ? reinterpret_cast<float*>(base + dst.offset) : nullptr;
+    if (d.residual >= 0) {
+      const BufferInfo& rb = e->bufs[d.residual];
+      p.res = reinterpret_cast<const __half*>(base + rb.offset);
+      p.res_up = d.residual_up; p.res_c = rb.channels; p.res_h = rb.h; p.res_w = rb.w; p.res_plane_elems = rb.plane_elems;
+    }
+    launch_conv(p, op);
     ++n_launch;
     CNL_CUDA_CHECK(cudaGetLastError());
-    (void)src;
   }
   if (launches) *launches = n_launch;
   return CNL_OK;
