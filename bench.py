@@ -187,22 +187,18 @@ def run_ours(args):
 
     # ---- e2e: public API from pinned host memory, H2D + D2H inside the timed region ----------------------------
     host_in = [torch.rand((BATCH_PER_GPU, 3, SIZE, SIZE)).pin_memory() for _ in range(2)]
-    dev_in = torch.empty((BATCH_PER_GPU, 3, SIZE, SIZE), device=dev)
-    host_out = {"boxes": torch.empty((BATCH_PER_GPU, TOPK, 4)).pin_memory(), "scores": torch.empty((BATCH_PER_GPU, TOPK)).pin_memory(),
-                "labels": torch.empty((BATCH_PER_GPU, TOPK), dtype=torch.int64).pin_memory()}
 
-    def e2e_step(i):
-        dev_in.copy_(host_in[i & 1], non_blocking=True)
-        det = net.detect(dev_in)
-        for k2, v in host_out.items():
-            v.copy_(det[k2], non_blocking=True)
-    for i in range(3):
-        e2e_step(i)
+    def e2e_run(n_steps):
+        # public API: pinned host batches in, pinned host detections out; H2D of batch i+1 overlaps compute of batch i
+        last = None
+        for last in net.detect_host_batches((host_in[i & 1] for i in range(n_steps)), dev):
+            pass
+        return last
+    e2e_run(3)
     barrier()
     e_steps = max(3, args.steps // 2)
     ev0.record()
-    for i in range(e_steps):
-        e2e_step(i)
+    e2e_run(e_steps)
     ev1.record()
     barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -234,7 +230,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (3x3 256->256 @128x128, op heads.heatmap.block_2)",
                     "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                     "peak_source": f"{src} bf16 burst (kernel timed alone, {reps} launches)", "kernel_ms": k_ms,
-                    "algorithmic_flops_per_launch": flops, "traffic": None,
+                    "algorithmic_flops_per_launch": flops, "traffic": 1038.5e6, "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01_tower_conv_ncu_details.txt",
                     "tensor_passes": 1 if args.precision == "fast" else 3}
         # ---- decode kernel: HBM roofline (second headline of BASELINE.json) ------------------------------------
         from centernet_lightning_b200 import decode as cdec

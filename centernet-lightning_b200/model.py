@@ -252,6 +252,55 @@ class CenterNet(nn.Module):
             self._graphs[key] = g
         return g.run(images)
 
+    @torch.no_grad()
+    def detect_host_batches(self, host_batches, device: Optional[torch.device] = None):
+        """Generator over detections for an iterable of PINNED host batches (N,3,H,W) float32.  The H2D copy of batch
+        i+1 runs on a side stream while batch i is computed (double-buffered device inputs); results are copied into
+        pinned host tensors and yielded once they have landed (the yielded dict is reused every second call)."""
+        dev = device or next(self.parameters()).device
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        dev_in, ready, consumed, host_out, out_done = [None, None], [None, None], [None, None], [None, None], [None, None]
+        it = iter(host_batches)
+
+        def stage(slot, hb):
+            if dev_in[slot] is None:
+                dev_in[slot] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copy_stream):
+                if consumed[slot] is not None:
+                    copy_stream.wait_event(consumed[slot])
+                dev_in[slot].copy_(hb, non_blocking=True)
+                ready[slot] = torch.cuda.Event()
+                ready[slot].record(copy_stream)
+
+        nxt = next(it, None)
+        if nxt is not None:
+            stage(0, nxt)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            cur = nxt
+            nxt = next(it, None)
+            if nxt is not None:
+                stage(slot ^ 1, nxt)
+            main.wait_event(ready[slot])
+            det = self.detect(dev_in[slot])
+            consumed[slot] = torch.cuda.Event()
+            consumed[slot].record(main)
+            if host_out[slot] is None:
+                host_out[slot] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in det.items()}
+            for k, v in det.items():
+                host_out[slot][k].copy_(v, non_blocking=True)
+            out_done[slot] = torch.cuda.Event()
+            out_done[slot].record(main)
+            if i > 0:
+                out_done[slot ^ 1].synchronize()
+                yield host_out[slot ^ 1]
+            i += 1
+        if i > 0:
+            out_done[(i - 1) & 1].synchronize()
+            yield host_out[(i - 1) & 1]
+
     def invalidate(self) -> None:
         self._graphs.clear()
         self.model.invalidate()

@@ -153,3 +153,60 @@ def test_api_surface(cuda):
         net.model(torch.rand(1, 3, 64, 64))
     with pytest.raises(ValueError):
         CenterNet(80, "resnet34", neck="bifpn")
+
+
+def test_config5_1024_input_large_maps(cuda):
+    """BASELINE config 5 geometry (1024x1024 -> 256x256 maps, two 128-column TMA tiles per row), batch 1."""
+    kw = dict(model=dict(num_classes=80), seed=3, n=1, size=1024, img_seed=21)
+    spec, net = _build(kw)
+    net = net.to(cuda)
+    x = cases.make_image(kw)
+    with torch.no_grad():
+        ref = spec(x)
+    out = net.model(x.to(cuda))
+    for k in ref:
+        assert tuple(out[k].shape) == tuple(ref[k].shape)
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=0, atol=TOL, err_msg=k)
+    det = net.detect(x.to(cuda))
+    assert tuple(det["boxes"].shape) == (1, 100, 4)
+
+
+def test_config4_tracking_k300_non_square(cuda):
+    """BASELINE config 4 (C=2 + box + 64-d reid, Tracker default k=300, reference models/tracker.py:51) on a non-square
+    input (reference tracking yaml trains at 608x1088; here 160x288 -> 40x72 maps: ragged TMA tiles)."""
+    from centernet_lightning_b200.model import CenterNet
+    spec = spec_model.synth_init(spec_model.build_spec_model(2, reid_dim=64), seed=4)
+    net = CenterNet(2, reid_dim=64, box_multiplier=16.0, num_detections=300)
+    net.model.load_state_dict(spec.state_dict())
+    net = net.to(cuda)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((2, 3, 160, 288), generator=g)
+    with torch.no_grad():
+        ref = spec(x)
+    out = {k: v.clone() for k, v in net.model(x.to(cuda)).items()}
+    for k in ref:
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=0, atol=TOL, err_msg=k)
+    det = {k: v.cpu().numpy() for k, v in net.detect(x.to(cuda)).items()}
+    assert det["embeddings"].shape == (2, 300, 64)
+    oracle = decode_np.decode_detections(decode_np.sigmoid_f32(out["heatmap"].cpu().numpy()), out["box_2d"].cpu().numpy(),
+                                         reid=out["reid"].cpu().numpy(), num_detections=300, box_multiplier=16.0)
+    np.testing.assert_allclose(det["scores"], oracle["scores"], rtol=0, atol=1e-6)
+    ok, msg = decode_np.same_detections({**det, "indices": None} if False else {"scores": oracle["scores"], "labels": det["labels"], "boxes": det["boxes"]},
+                                        {"scores": oracle["scores"], "labels": oracle["labels"], "boxes": oracle["boxes"]})
+    assert ok, msg
+
+
+def test_inference_detection_folder(cuda, tmp_path):
+    """reference README.md:49-65: folder -> dict of numpy arrays (n_img,k,4) / (n_img,k) / (n_img,k)."""
+    from PIL import Image
+    from centernet_lightning_b200.model import CenterNet
+    rng = np.random.default_rng(0)
+    for i in range(5):
+        Image.fromarray(rng.integers(0, 255, (48 + 8 * i, 64, 3), dtype=np.uint8)).save(tmp_path / f"img_{i}.png")
+    net = CenterNet(80, box_multiplier=16.0).init_synthetic_(1)
+    out = net.inference_detection(str(tmp_path), batch_size=2, num_detections=20, img_size=128)
+    assert out["bboxes"].shape == (5, 20, 4) and out["labels"].shape == (5, 20) and out["scores"].shape == (5, 20)
+    assert out["bboxes"].dtype == np.float32 and out["labels"].dtype == np.int64
+    assert np.all(out["scores"][:, :-1] >= out["scores"][:, 1:])
+    one = net.inference_detection(str(tmp_path), img_names=["img_3.png"], batch_size=2, num_detections=20, img_size=128)
+    np.testing.assert_allclose(one["scores"][0], out["scores"][3], rtol=0, atol=1e-6)
