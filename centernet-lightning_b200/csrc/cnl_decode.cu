@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cuda.h>
 #include "cnl_common.h"
 
 namespace cnl {
@@ -188,19 +189,8 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
   }
 }
 
-// ---- interior fast path: per-warp ring of bulk async copies (cp.async.bulk + mbarrier) -----------------------
-// Each warp streams its classes through a private 2-stage shared-memory ring: lane 0 arms a stage with one
-// mbarrier.expect_tx and ROWS 512-byte bulk copies (one per map row), every lane then reads its float4 with one
-// LDS.128 per row.  Bytes in flight per SM are set by the ring (2 stages x 3 KB x 28 warps), not by registers.
+// ---- mbarrier helpers (used by the TMA-fed variant below) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-// W == kTW: the ROWS rows of a strip are contiguous in the class plane, so one bulk copy brings the whole stage.
-__device__ __forceinline__ void ring_arm(float* stage_smem, uint64_t* bar, const float* gsrc, int rows, int /*W*/) {
-  const uint32_t b = smem_addr_u32(bar);
-  const uint32_t bytes = rows * 512;
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_addr_u32(stage_smem)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
-}
 __device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -213,85 +203,10 @@ __device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int P, bool LOGITS, int R>
-__device__ __forceinline__ void peaks_class_loop_bulk(const float* __restrict__ tile_base /* row r0-P, first column of the tile */,
-                                                      size_t plane, int c_begin, int c_end, int W, int lane,
-                                                      float* ring /*[2][ROWS][128]*/, uint64_t* bars /*[2]*/,
-                                                      float (&best)[R][4], int (&lab)[R][4]) {
-  constexpr int ROWS = R + 2 * P;
-  const float NEG = -INFINITY;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (c_begin + s < c_end) ring_arm(ring + s * ROWS * kTW, bars + s, tile_base + (size_t)(c_begin + s) * plane, ROWS, W);
-  }
-#pragma unroll 1
-  for (int c = c_begin; c < c_end; ++c) {
-    const int it = c - c_begin;
-    const int s = it & 1;
-    ring_wait(bars + s, (it >> 1) & 1);
-    const float* st = ring + s * ROWS * kTW + lane * 4;
-    float4 v[ROWS];
-#pragma unroll
-    for (int j = 0; j < ROWS; ++j) v[j] = *reinterpret_cast<const float4*>(st + j * kTW);
-    // vertical window max for every output row: consumes all loaded rows, so the stage can be re-armed afterwards
-    float4 vm[R];
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      vm[i] = v[i];
-#pragma unroll
-      for (int j = 1; j <= 2 * P; ++j) vm[i] = max4(vm[i], v[i + j]);
-    }
-    if (LOGITS) {
-      // saturation clamp (see kSatLogit) only when some logit of this warp's strip reaches it - rare in practice
-      float4 t4 = vm[0];
-#pragma unroll
-      for (int i = 1; i < R; ++i) t4 = max4(t4, vm[i]);
-      const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
-      if (__any_sync(0xffffffffu, tmax >= kSatLogit)) {
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j)
-          v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          vm[i] = v[i];
-#pragma unroll
-          for (int j = 1; j <= 2 * P; ++j) vm[i] = max4(vm[i], v[i + j]);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0 && c + 2 < c_end) ring_arm(ring + s * ROWS * kTW, bars + s, tile_base + (size_t)(c + 2) * plane, ROWS, W);
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      float e[4 + 2 * P];
-      e[P + 0] = vm[i].x; e[P + 1] = vm[i].y; e[P + 2] = vm[i].z; e[P + 3] = vm[i].w;
-      if constexpr (P > 0) {
-        const float own[4] = {vm[i].x, vm[i].y, vm[i].z, vm[i].w};
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-          float fl = __shfl_sync(0xffffffffu, own[3 - q], (lane + 31) & 31);
-          float fr = __shfl_sync(0xffffffffu, own[q], (lane + 1) & 31);
-          e[P - 1 - q] = (lane == 0) ? NEG : fl;
-          e[P + 4 + q] = (lane == 31) ? NEG : fr;
-        }
-      }
-      const float ctr[4] = {v[i + P].x, v[i + P].y, v[i + P].z, v[i + P].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float m = e[j];
-#pragma unroll
-        for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[j + q]);
-        update_cand<LOGITS>(best[i][j], lab[i][j], ctr[j], m, c);
-      }
-    }
-  }
-}
-
 template <int P, bool LOGITS, int R, int G, bool MT>
 __global__ void __launch_bounds__(G * 32, (G == 4) ? 7 : 8)
 peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, uint16_t* __restrict__ clabel,
-                  unsigned int* __restrict__ hist, int C, int H, int W, int use_bulk) {
+                  unsigned int* __restrict__ hist, int C, int H, int W) {
   const int lane = threadIdx.x & 31;
   const int g = threadIdx.x >> 5;
   const int n = blockIdx.z;
@@ -312,37 +227,15 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
 
   const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
   const bool interior = (r0 - P >= 0) && (r0 + R + P <= H) && ((int)(blockIdx.x + 1) * kTW <= W);   // block-uniform
-  constexpr int ROWS = R + 2 * P;
-  constexpr int kRingFloats = MT ? 0 : G * 2 * ROWS * kTW;
   constexpr int kMergeBytes = G * R * kTW * 6;
-  constexpr int kSmemBytes = (kRingFloats * 4 > kMergeBytes) ? kRingFloats * 4 : kMergeBytes;
-  __shared__ __align__(128) unsigned char s_raw[kSmemBytes];
-  __shared__ __align__(8) uint64_t s_bars[G][2];
-  if constexpr (!MT) {
-    if (interior && W == kTW && use_bulk) {
-      if (lane == 0) {
-        for (int s2 = 0; s2 < 2; ++s2)
-          asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_bars[g][s2])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-      __syncwarp();
-      float* ring = reinterpret_cast<float*>(s_raw) + g * 2 * ROWS * kTW;
-      peaks_class_loop_bulk<P, LOGITS, R>(base - lane * 4, plane, c_begin, c_end, W, lane, ring, &s_bars[g][0], best, lab);
-    } else if (interior) {
-      peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
-    } else {
-      peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
-    }
-  } else {
-    if (interior) peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
-    else          peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
-  }
+  __shared__ __align__(128) unsigned char s_raw[kMergeBytes];
+  if (interior) peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
+  else          peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
 
-  // merge the G class groups (in class order) through shared memory (aliases the ring), then emit one candidate per pixel
+  // merge the G class groups (in class order) through shared memory, then emit one candidate per pixel
   float (*s_v)[R][kTW] = reinterpret_cast<float (*)[R][kTW]>(s_raw);
   uint16_t (*s_l)[R][kTW] = reinterpret_cast<uint16_t (*)[R][kTW]>(s_raw + G * R * kTW * 4);
   if (G > 1) {
-    __syncthreads();                        // every warp is done with its ring stages
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
@@ -376,6 +269,150 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
     *reinterpret_cast<float4*>(cscore + o) = make_float4(sc[0], sc[1], sc[2], sc[3]);
     ushort4 l4 = make_ushort4((uint16_t)lb[0], (uint16_t)lb[1], (uint16_t)lb[2], (uint16_t)lb[3]);
     *reinterpret_cast<ushort4*>(clabel + o) = l4;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel 1a': TMA-fed peaks kernel for the common geometry (W == 128, nms 3x3, C % 4 == 0).
+//   CTA = one 4-row strip of one image, 4 warps.  A 2-stage shared-memory ring is filled by ONE 3-D tensor-map load
+//   per stage: box {128 columns, 6 rows, 4 classes} = 12 KB (rows r0-1..r0+4 of four consecutive class planes).  Warp g
+//   consumes class 4*it+g of every stage (pulls it into registers at once, so the stage is refilled immediately).
+//   Bytes in flight per SM are set by the ring (2 stages x 12 KB x 7 CTAs = 168 KB) instead of by registers, and the load path costs one elected-thread instruction per 12 KB.
+//   Strips touching the top/bottom border (-inf padding, which TMA zero-fill cannot express) use the LDG loop.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 2;
+constexpr int kTmaClasses = 4;       // classes per stage = warps per CTA
+
+template <bool LOGITS>
+__global__ void __launch_bounds__(128, 7)
+peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __restrict__ heat, float* __restrict__ cscore,
+                 uint16_t* __restrict__ clabel, unsigned int* __restrict__ hist, int C, int H, int W) {
+  constexpr int P = 1, R = 4, G = 4, ROWS = R + 2 * P;
+  constexpr int kStageFloats = kTmaClasses * ROWS * kTW;             // 3072 floats = 12 KB
+  __shared__ __align__(128) float s_ring[kTmaStages * kStageFloats];
+  __shared__ __align__(8) uint64_t s_full[kTmaStages];
+  __shared__ __align__(8) uint64_t s_empty[kTmaStages];
+  const int lane = threadIdx.x & 31;
+  const int g = threadIdx.x >> 5;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * R;
+  const int x0 = lane * 4;
+  const size_t plane = (size_t)H * W;
+  const float NEG = -INFINITY;
+
+  float best[R][4];
+  int lab[R][4];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { best[i][j] = NEG; lab[i][j] = 0; }
+
+  const bool interior = (r0 - P >= 0) && (r0 + R + P <= H);          // block-uniform
+  if (interior) {
+    const int n_it = C / kTmaClasses;
+    if (threadIdx.x == 0) {
+      for (int s2 = 0; s2 < kTmaStages; ++s2) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_full[s2])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&s_empty[s2])), "r"(G) : "memory");
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto arm = [&](int it) {
+      const int s2 = it % kTmaStages;
+      const uint32_t bar = smem_addr_u32(&s_full[s2]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageFloats * 4) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                   ::"r"(smem_addr_u32(s_ring + s2 * kStageFloats)), "l"(reinterpret_cast<uint64_t>(&heat_map)), "r"(bar),
+                     "r"(0), "r"(r0 - P), "r"(n * C + it * kTmaClasses) : "memory");
+    };
+    if (threadIdx.x == 0) {
+      arm(0);
+      if (n_it > 1) arm(1);
+    }
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const int s2 = it % kTmaStages;
+      const int c = it * kTmaClasses + g;
+      ring_wait(&s_full[s2], (it / kTmaStages) & 1);
+      const float* st = s_ring + s2 * kStageFloats + g * ROWS * kTW + lane * 4;
+      float4 v[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) v[j] = *reinterpret_cast<const float4*>(st + j * kTW);
+      float4 vm[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) vm[i] = max4(max4(v[i], v[i + 1]), v[i + 2]);
+      if (LOGITS) {
+        float4 t4 = max4(max4(vm[0], vm[1]), max4(vm[2], vm[3]));
+        const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
+        if (__any_sync(0xffffffffu, tmax >= kSatLogit)) {            // saturation clamp, rare (see kSatLogit)
+#pragma unroll
+          for (int j = 0; j < ROWS; ++j)
+            v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
+#pragma unroll
+          for (int i = 0; i < R; ++i) vm[i] = max4(max4(v[i], v[i + 1]), v[i + 2]);
+        }
+      }
+      __syncwarp();                                                  // every lane's stage reads are consumed (vm depends on them)
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(&s_empty[s2])) : "memory");
+      // producer duty of thread 0: once all 4 warps have pulled this stage into registers, refill it two classes-groups ahead
+      if (threadIdx.x == 0 && it + kTmaStages < n_it) {
+        ring_wait(&s_empty[s2], (it / kTmaStages) & 1);
+        arm(it + kTmaStages);
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        float fl = __shfl_sync(0xffffffffu, vm[i].w, (lane + 31) & 31);
+        float fr = __shfl_sync(0xffffffffu, vm[i].x, (lane + 1) & 31);
+        fl = (lane == 0) ? NEG : fl;
+        fr = (lane == 31) ? NEG : fr;
+        const float e[6] = {fl, vm[i].x, vm[i].y, vm[i].z, vm[i].w, fr};
+        const float ctr[4] = {v[i + 1].x, v[i + 1].y, v[i + 1].z, v[i + 1].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) update_cand<LOGITS>(best[i][j], lab[i][j], ctr[j], fmaxf(fmaxf(e[j], e[j + 1]), e[j + 2]), c);
+      }
+    }
+  } else {
+    const int cg = (C + G - 1) / G;
+    const int c_begin = g * cg, c_end = min(C, c_begin + cg);
+    const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
+    peaks_class_loop<P, LOGITS, R, false, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, true, best, lab);
+  }
+
+  // merge the 4 warps' winners: maximal value, lowest class on ties (= first maximal class of torch.max)
+  __syncthreads();                                                   // ring no longer in use: alias it
+  float (*s_v)[R][kTW] = reinterpret_cast<float (*)[R][kTW]>(s_ring);
+  uint16_t (*s_l)[R][kTW] = reinterpret_cast<uint16_t (*)[R][kTW]>(s_ring + G * R * kTW);
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
+    *reinterpret_cast<ushort4*>(&s_l[g][i][lane * 4]) =
+        make_ushort4((uint16_t)lab[i][0], (uint16_t)lab[i][1], (uint16_t)lab[i][2], (uint16_t)lab[i][3]);
+  }
+  __syncthreads();
+  {
+    const int i = g;                                                 // warp g finishes row g (R == G)
+    const int r = r0 + i;
+    if (r < H) {
+      float sc[4];
+      int lb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float bv = s_v[0][i][lane * 4 + j];
+        int bl = s_l[0][i][lane * 4 + j];
+#pragma unroll
+        for (int gg = 1; gg < G; ++gg) {
+          const float ov = s_v[gg][i][lane * 4 + j];
+          const int ol = s_l[gg][i][lane * 4 + j];
+          if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+        }
+        finish_cand<LOGITS>(bv, bl, sc[j], lb[j]);
+        atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(sc[j]) >> kHistShift), 1u);
+      }
+      const size_t o = (size_t)n * plane + (size_t)r * W + x0;
+      *reinterpret_cast<float4*>(cscore + o) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+      *reinterpret_cast<ushort4*>(clabel + o) = make_ushort4((uint16_t)lb[0], (uint16_t)lb[1], (uint16_t)lb[2], (uint16_t)lb[3]);
+    }
   }
 }
 
@@ -575,6 +612,9 @@ __device__ void radix_select_fallback(const float* sc, int HW, int k, unsigned l
   __syncthreads();
 }
 
+// CACHE: H*W <= 16384 and a multiple of 4 - every thread keeps its 16 candidates in registers (loaded once, before
+// the histogram scan, so the L2 latency hides behind it); otherwise the passes re-read the candidate map from L2.
+template <bool CACHE>
 __global__ void __launch_bounds__(kSelThreads)
 select_gather_kernel(DecodeParams p) {
   __shared__ unsigned long long s_list[kListCap];
@@ -588,6 +628,40 @@ select_gather_kernel(DecodeParams p) {
   const int HW = p.H * p.W;
   const float* sc = p.cscore + (size_t)n * HW;
   const int k = p.k;
+  const bool vec4 = (HW & 3) == 0;
+  const float4* sc4 = reinterpret_cast<const float4*>(sc);
+  const int n_vec = vec4 ? (HW >> 2) : 0;
+
+  float4 cache[4];
+  if (CACHE) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * kSelThreads;
+      cache[q] = (i < n_vec) ? sc4[i] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);   // -inf sorts below every candidate
+    }
+  }
+  // visit(f): f(key, flat_index) for every candidate of this thread
+  auto visit = [&](auto&& f) {
+    if (CACHE) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + q * kSelThreads;
+        if (i < n_vec) {
+          const float fv[4] = {cache[q].x, cache[q].y, cache[q].z, cache[q].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j);
+        }
+      }
+    } else {
+      for (int i = tid; i < n_vec; i += kSelThreads) {
+        const float4 v4 = sc4[i];
+        const float fv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j);
+      }
+      for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) f(sortable_key(sc[i]), i);
+    }
+  };
 
   // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
   const uint4 h4 = *reinterpret_cast<const uint4*>(p.hist + (size_t)n * kHistBins + (kHistBins - 4 - 4 * tid));
@@ -605,27 +679,14 @@ select_gather_kernel(DecodeParams p) {
   __syncthreads();
   const uint32_t bin_k = (uint32_t)s_scalars[0];
   const int n_in_or_above = s_scalars[1];
-  const bool vec4 = (HW & 3) == 0;
-  const float4* sc4 = reinterpret_cast<const float4*>(sc);
-  const int n_vec = vec4 ? (HW >> 2) : 0;
   __syncthreads();                                  // everyone has read s_scalars before it is reused
   int n_sort;
   bool done = false;
   if (n_in_or_above <= kRefineAbove) {
     // few enough: collect every candidate in bin_k or above and sort them all
-    for (int i = tid; i < n_vec; i += kSelThreads) {
-      const float4 f = sc4[i];
-      const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t u = sortable_key(fv[j]);
-        if ((u >> kHistShift) >= bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, 4 * i + j);
-      }
-    }
-    for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) {
-      const uint32_t u = sortable_key(sc[i]);
+    visit([&](uint32_t u, int i) {
       if ((u >> kHistShift) >= bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
-    }
+    });
     n_sort = n_in_or_above;
     done = true;
   } else {
@@ -634,23 +695,11 @@ select_gather_kernel(DecodeParams p) {
     // of bin_k at or above the sub-bin that holds the k-th largest.
     for (int i = tid; i < kBins; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n_vec; i += kSelThreads) {
-      const float4 f = sc4[i];
-      const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t u = sortable_key(fv[j]);
-        const uint32_t b = u >> kHistShift;
-        if (b > bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, 4 * i + j);
-        else if (b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
-      }
-    }
-    for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) {
-      const uint32_t u = sortable_key(sc[i]);
+    visit([&](uint32_t u, int i) {
       const uint32_t b = u >> kHistShift;
       if (b > bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
       else if (b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
-    }
+    });
     __syncthreads();
     const int n_above = s_n;                         // < k by construction
     const int need = k - n_above;
@@ -666,20 +715,9 @@ select_gather_kernel(DecodeParams p) {
     const uint32_t sub_k = (uint32_t)s_scalars[0];
     const int n_total = n_above + s_scalars[1];
     if (n_total <= kListCap) {
-      for (int i = tid; i < n_vec; i += kSelThreads) {
-        const float4 f = sc4[i];
-        const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t u = sortable_key(fv[j]);
-          if ((u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k)
-            s_list[atomicAdd(&s_n, 1)] = pack_entry(u, 4 * i + j);
-        }
-      }
-      for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) {
-        const uint32_t u = sortable_key(sc[i]);
+      visit([&](uint32_t u, int i) {
         if ((u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
-      }
+      });
       n_sort = n_total;
       done = true;
     }
@@ -741,13 +779,10 @@ static void launch_fast(const float* heat, float* cscore, uint16_t* clabel, unsi
   constexpr int R = 4;
   dim3 grid((W + kTW - 1) / kTW, (H + R - 1) / R, N);
   const bool mt = grid.x > 1;        // rows wider than one 128-column warp tile need halo columns from neighbours
-  // CNL_PEAKS_BULK=1 selects the cp.async.bulk + mbarrier ring for interior strips (measured 49 us vs 43 us for the
-  // register-prefetch path at 32x80x128x128 on B200, so it is off by default; kept for tuning).
-  static const int use_bulk = (getenv("CNL_PEAKS_BULK") && atoi(getenv("CNL_PEAKS_BULK")) != 0) ? 1 : 0;
 #define CNL_LAUNCH_PEAKS(G_)                                                                                      \
   do {                                                                                                            \
-    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W, use_bulk);  \
-    else    peaks_fast_kernel<P, LOGITS, R, G_, false><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W, use_bulk); \
+    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W);  \
+    else    peaks_fast_kernel<P, LOGITS, R, G_, false><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W); \
   } while (0)
   if (C >= 32) CNL_LAUNCH_PEAKS(4);
   else if (C >= 2) CNL_LAUNCH_PEAKS(2);
@@ -755,9 +790,42 @@ static void launch_fast(const float* heat, float* cscore, uint16_t* clabel, unsi
 #undef CNL_LAUNCH_PEAKS
 }
 
+typedef CUresult (*EncodeTiledFnD)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D fp32 tensor map over the heatmap viewed as [N*C][H][W] with box {128, 6, 4}; false if the driver entry is missing.
+static bool make_heat_map(CUtensorMap* m, const float* heat, int N, int C, int H, int W) {
+  static EncodeTiledFnD fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+    fn = reinterpret_cast<EncodeTiledFnD>(p);
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * C};
+  cuuint64_t str[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kTW, 6, (cuuint32_t)kTmaClasses};
+  cuuint32_t es[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(heat), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <bool LOGITS>
 static void launch_peaks(const float* heat, float* cscore, uint16_t* clabel, unsigned int* hist, int N, int C, int H, int W,
                          int P, bool force_generic, cudaStream_t st) {
+  // CNL_PEAKS_TMA=1 selects the TMA-fed kernel (measured 50 us vs 43 us for the register-prefetch kernel at
+  // 32x80x128x128 on B200: the pass is bounded by the 1.5x halo re-reads at L2, not by bytes in flight; kept for tuning).
+  static const int use_tma = (getenv("CNL_PEAKS_TMA") && atoi(getenv("CNL_PEAKS_TMA")) != 0) ? 1 : 0;
+  if (!force_generic && use_tma && P == 1 && W == kTW && H % 4 == 0 && H >= 12 && C % kTmaClasses == 0 &&
+      ((reinterpret_cast<uintptr_t>(heat) & 15) == 0)) {
+    CUtensorMap m;
+    if (make_heat_map(&m, heat, N, C, H, W)) {
+      dim3 grid(1, H / 4, N);
+      peaks_tma_kernel<LOGITS><<<grid, 128, 0, st>>>(m, heat, cscore, clabel, hist, C, H, W);
+      return;
+    }
+  }
   bool fast = !force_generic && (W % 4 == 0) && P <= 2 && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   if (fast) {
     switch (P) {
@@ -838,7 +906,8 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   p.normalize = normalize_boxes; p.box_log = box_log; p.mult = box_multiplier; p.stride_f = (float)stride;
   p.boxes = boxes; p.scores = scores; p.labels = reinterpret_cast<long long*>(labels);
   p.indices = reinterpret_cast<long long*>(indices); p.emb = embeddings;
-  select_gather_kernel<<<n, kSelThreads, 0, st>>>(p);
+  if ((h * w) % 4 == 0 && h * w <= 4 * 4 * kSelThreads) select_gather_kernel<true><<<n, kSelThreads, 0, st>>>(p);
+  else                                                  select_gather_kernel<false><<<n, kSelThreads, 0, st>>>(p);
   CNL_CUDA_CHECK(cudaGetLastError());
   return CNL_OK;
 }

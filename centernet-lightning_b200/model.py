@@ -315,6 +315,8 @@ class CenterNet(nn.Module):
             if isinstance(mod, nn.Conv2d):
                 fan_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1]
                 mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
+                if name.endswith("out_conv"):
+                    mod.weight.mul_(0.2)             # head logits with std ~1.5 around the prior, like a trained heatmap
                 if mod.bias is not None and not name.endswith("heatmap.out_conv"):
                     mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
             elif isinstance(mod, nn.BatchNorm2d):
