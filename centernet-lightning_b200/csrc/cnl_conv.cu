@@ -60,6 +60,7 @@ struct ConvParams {
   long long res_plane_elems;
   int num_stages;
   int store_w, store_h;         // per-warp TMA store box in pixels (store_w * store_h == 32)
+  int cluster;                  // CTAs per cluster sharing one multicast weight tile (1 = no cluster)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -89,13 +90,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;        // [4 warps][NPLANE][4096], 1024-aligned
   const int taps = p.kh * p.kw;
   const int k_iters = taps * p.kblocks;
-  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&src_map);
     ptx::prefetch_tmap(&w_map);
     if (p.out_mode == 0) ptx::prefetch_tmap(&dst_map);
-    for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], p.cluster); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], 4); }
     ptx::fence_barrier_init();
   }
@@ -105,19 +105,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync_all();       // peers' barriers are initialised before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // Work distribution.  A cluster of `csize` CTAs takes `csize` consecutive pixel tiles of the SAME Cout tile, so the
+  // weight tile is fetched from L2 once per cluster: CTA r loads rows [r, r+1) * n_tile/csize and multicasts them.
+  // A pixel tile past the end (m_tiles not a multiple of csize) is a dummy: its image coordinate is out of bounds, so
+  // TMA loads return zeros and stores are clipped, while the CTA keeps its part in the shared barrier protocol.
+  const int csize = p.cluster;
+  const int crank = (csize > 1) ? (int)ptx::cluster_ctarank() : 0;
+  const int m_groups = (p.m_tiles + csize - 1) / csize;
+  const int total_groups = m_groups * p.n_tiles;
+  const int group0 = blockIdx.x / csize, group_step = gridDim.x / csize;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
     // ===================================== TMA producer ==============================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % p.n_tiles;
-        int m_idx = tile / p.n_tiles;
-        const int img = m_idx / (p.tiles_h * p.tiles_w);
-        m_idx -= img * (p.tiles_h * p.tiles_w);
+      const int b_rows = p.n_tile / csize;
+      for (int grp = group0; grp < total_groups; grp += group_step) {
+        const int n_idx = grp % p.n_tiles;
+        int m_idx = (grp / p.n_tiles) * csize + crank;
+        int img = m_idx / tiles_per_img;
+        m_idx -= img * tiles_per_img;
+        if (img >= p.n_img) img = 1 << 20;                // dummy tile: every coordinate out of bounds
         const int h0 = (m_idx / p.tiles_w) * p.th;
         const int w0 = (m_idx % p.tiles_w) * p.tw;
         for (int tap = 0; tap < taps; ++tap) {
@@ -132,10 +146,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             for (int pl = 0; pl < NPLANE; ++pl)
               ptx::tma_load_4d(st + pl * kATileBytes, &src_map, &full_bar[stage], p.src_c_off + kb * kBlockK, cw, ch,
                                img + pl * p.n_img);
+            if (csize == 1) {
 #pragma unroll
-            for (int pl = 0; pl < NPLANE; ++pl)
-              ptx::tma_load_3d(st + NPLANE * kATileBytes + pl * b_tile_bytes, &w_map, &full_bar[stage], kb * kBlockK,
-                               n_idx * p.n_tile, tap + pl * taps);
+              for (int pl = 0; pl < NPLANE; ++pl)
+                ptx::tma_load_3d(st + NPLANE * kATileBytes + pl * b_tile_bytes, &w_map, &full_bar[stage], kb * kBlockK,
+                                 n_idx * p.n_tile, tap + pl * taps);
+            } else {
+#pragma unroll
+              for (int pl = 0; pl < NPLANE; ++pl)
+                ptx::tma_load_3d_mc(st + NPLANE * kATileBytes + pl * b_tile_bytes + crank * b_rows * (kBlockK * 2), &w_map,
+                                    &full_bar[stage], kb * kBlockK, n_idx * p.n_tile + crank * b_rows, tap + pl * taps, cmask);
+            }
             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -148,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int acc_it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+      for (int grp = group0; grp < total_groups; grp += group_step, ++acc_it) {
         const int as = CORR ? 0 : (acc_it & 1);
         const uint32_t aphase = CORR ? (acc_it & 1) : ((acc_it >> 1) & 1);
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
@@ -173,7 +194,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);          // smem stage reusable once these MMAs retire
+          if (csize == 1) ptx::umma_commit(&empty_bar[stage]);          // smem stage reusable once these MMAs retire
+          else            ptx::umma_commit_mc(&empty_bar[stage], cmask); // ... in every CTA of the cluster (shared weight tile)
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tmem_full_bar[as]);           // accumulator complete -> epilogue
@@ -185,18 +207,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const int lane_base = q * 32;
     uint8_t* my_stage = staging + (size_t)(warp - 2) * NPLANE * kStageWarpBytes;
     int acc_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+    for (int grp = group0; grp < total_groups; grp += group_step, ++acc_it) {
       const int as = CORR ? 0 : (acc_it & 1);
       const uint32_t aphase = CORR ? (acc_it & 1) : ((acc_it >> 1) & 1);
-      const int n_idx = tile % p.n_tiles;
-      int m_idx = tile / p.n_tiles;
-      const int img = m_idx / (p.tiles_h * p.tiles_w);
-      m_idx -= img * (p.tiles_h * p.tiles_w);
+      const int n_idx = grp % p.n_tiles;
+      int m_idx = (grp / p.n_tiles) * csize + crank;
+      int img = m_idx / tiles_per_img;
+      m_idx -= img * tiles_per_img;
+      const bool dummy = img >= p.n_img;
+      if (dummy) img = 1 << 20;
       const int h0 = (m_idx / p.tiles_w) * p.th;
       const int w0 = (m_idx % p.tiles_w) * p.tw;
       const int pix = lane_base + lane;
       const int h = h0 + pix / p.tw, w = w0 + pix % p.tw;
-      const bool valid = (h < p.out_h) && (w < p.out_w);
+      const bool valid = !dummy && (h < p.out_h) && (w < p.out_w);
 
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
@@ -327,6 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) ptx::cluster_sync_all();       // no peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -489,7 +514,7 @@ struct BufferInfo {
 struct OpInfo {
   cnl_conv_desc d;
   // conv
-  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h;
+  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster;
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
   std::vector<__half> w_packed;       // [plane][tap][cout_pad][cin]
@@ -537,6 +562,17 @@ static int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* di
 
 static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+// CTAs per cluster that share one multicast weight tile.  Opt-in through CNL_CLUSTER=2 (or 4): measured on B200 the
+// kernel is tensor/power-bound, not L2-bound, so halving the weight traffic changes nothing (1.229 vs 1.220 ms on the
+// 256->256 tower conv; cluster 4 strands SMs and is slower); default 1.  Each CTA loads
+// n_tile/cluster weight rows, which must stay a multiple of the 8-row swizzle atom.
+static int choose_cluster(int n_tile, int m_tiles) {
+  static const int want = [] { const char* v = getenv("CNL_CLUSTER"); int c = v ? atoi(v) : 1; return (c == 1 || c == 2 || c == 4) ? c : 1; }();
+  int c = want;
+  while (c > 1 && (n_tile % (8 * c) != 0 || m_tiles < 2 * c)) c >>= 1;
+  return c;
+}
+
 static void split_half(float x, __half* hi, __half* lo) {
   *hi = __float2half_rn(x);
   *lo = __float2half_rn(x - __half2float(*hi));
@@ -581,6 +617,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   const int staging = dst.fp32_nchw ? 0 : 4 * planes * kStageWarpBytes;
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / stage_bytes);
   if (op.num_stages < 2) return fail(CNL_ERR_UNSUPPORTED, "conv tile does not fit shared memory");
+  op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = d.ksize * d.ksize;
@@ -631,6 +668,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   const int planes = e->planes;
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - 4 * planes * kStageWarpBytes) / stage_bytes);
+  op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
@@ -750,7 +788,7 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       if (r) return r;
       cuuint64_t wd[3] = {64, 64, (cuuint64_t)4 * planes};
       cuuint64_t ws[2] = {128, 64 * 128};
-      cuuint32_t wb[3] = {64, 64, 1};
+      cuuint32_t wb[3] = {64, (cuuint32_t)(64 / op.cluster), 1};
       cuuint32_t we[3] = {1, 1, 1};
       r = encode_map(&op.w_map, base + op.w_offset, 3, wd, ws, wb, we, "stem weights");
       if (r) return r;
@@ -772,7 +810,7 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
     {
       cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)op.cout_pad, (cuuint64_t)taps * planes};
       cuuint64_t str[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)op.cout_pad * d.cin * 2};
-      cuuint32_t box[3] = {64, (cuuint32_t)op.n_tile, 1};
+      cuuint32_t box[3] = {64, (cuuint32_t)(op.n_tile / op.cluster), 1};
       cuuint32_t es[3] = {1, 1, 1};
       int r = encode_map(&op.w_map, base + op.w_offset, 3, dims, str, box, es, "weights");
       if (r) return r;
@@ -801,12 +839,22 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
   uint8_t* base = static_cast<uint8_t*>(arena);
   const int planes = e->planes;
   int n_launch = 0;
-  auto launch_conv = [&](const ConvParams& p, const OpInfo& op) {
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    const int grid = std::min(total_tiles, e->num_sms);
-    if (e->precision == CNL_PRECISION_SPLIT)            conv_tc_kernel<2, true><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
-    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) conv_tc_kernel<2, false><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
-    else                                                conv_tc_kernel<1, false><<<grid, kConvThreads, kSmemLimit, st>>>(op.src_map, op.w_map, op.dst_map, p);
+  auto launch_conv = [&](const ConvParams& p, const OpInfo& op) -> cudaError_t {
+    const int groups = ((p.m_tiles + p.cluster - 1) / p.cluster) * p.n_tiles;
+    const int grid = p.cluster * std::min(groups, e->num_sms / p.cluster);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = kSmemLimit;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (e->precision == CNL_PRECISION_SPLIT)            return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true>, op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false>, op.src_map, op.w_map, op.dst_map, p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, op.src_map, op.w_map, op.dst_map, p);
   };
   for (int i = first_op; i < last_op; ++i) {
     OpInfo& op = e->ops[i];
@@ -821,7 +869,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.wscale_inv = 1.0f / op.wscale;
     p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
-    p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h;
+    p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
@@ -835,7 +883,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
       p.out_h = SH; p.out_w = SW;
       p.kh = 4; p.kw = 1; p.stride = 1; p.pad_h = 2; p.pad_w = 0; p.kblocks = 1;
       p.src_c_off = 0; p.dst_c_off = 0; p.out_mode = 0; p.cout_real = 64; p.out_nchw = nullptr;
-      launch_conv(p, op);
+      CNL_CUDA_CHECK(launch_conv(p, op));
       const long long total = (long long)e->batch * (SH / 2) * (SW / 2) * 8;
       const int b2 = (int)((total + 255) / 256);
       __half* o = reinterpret_cast<__half*>(base + dst.offset);
@@ -856,7 +904,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
       p.res = reinterpret_cast<const __half*>(base + rb.offset);
       p.res_up = d.residual_up; p.res_c = rb.channels; p.res_h = rb.h; p.res_w = rb.w; p.res_plane_elems = rb.plane_elems;
     }
-    launch_conv(p, op);
+    CNL_CUDA_CHECK(launch_conv(p, op));
     ++n_launch;
     CNL_CUDA_CHECK(cudaGetLastError());
   }

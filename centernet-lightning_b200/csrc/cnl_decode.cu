@@ -46,32 +46,18 @@ __device__ __forceinline__ float sigmoid32(float x) { return __fdiv_rn(1.0f, __f
 // the first saturated class wins the label).  Clamping logits at kSatLogit reproduces that plateau exactly.
 constexpr float kSatLogit = 17.0f;
 
-// x: centre value, m: kxk window max (m >= x), c: class.  Reference: mask = (maxpool(h) == h); h*mask; max over
-// classes with the first maximal class winning.
+// x: centre value, m: kxk window max (m >= x).  Reference: mask = (maxpool(h) == h); h*mask; max over classes.
+// The streaming pass keeps only the per-pixel MAXIMUM of the masked values (3 ALU ops per element); which class
+// attained it is recovered afterwards for the k winners only (select kernel), by the reference's rule "first class
+// whose masked value equals the maximum".
+// `best` starts at -inf for logits ("no peak yet" = probability 0) and at 0 for probabilities (a non-peak contributes
+// h*mask = 0; exact for non-negative inputs, i.e. probabilities).  One compare + one predicated max per element.
 template <bool LOGITS>
-__device__ __forceinline__ void update_cand(float& best, int& label, float x, float m, int c) {
-  if (LOGITS) {                       // best starts at -inf: "no peak yet"
-    bool take = (x == m) && (x > best);
-    best = take ? x : best;
-    label = take ? c : label;
-  } else {                            // exact h*mask semantics for any finite input: non-peaks contribute 0
-    float cand = (x == m) ? x : 0.0f;
-    bool take = cand > best;
-    best = take ? cand : best;
-    label = take ? c : label;
-  }
+__device__ __forceinline__ void masked_max(float& best, float x, float m) {
+  if (x == m) best = fmaxf(best, x);
 }
-
 template <bool LOGITS>
-__device__ __forceinline__ void finish_cand(float best, int lab, float& score, int& label) {
-  if (LOGITS) {
-    score = sigmoid32(best);                // -inf (no peak at this pixel) -> exactly 0; >= 17 -> exactly 1
-    label = (score == 0.0f) ? 0 : lab;      // an all-zero column arg-maxes to class 0 in the reference
-  } else {
-    score = best;
-    label = lab;
-  }
-}
+__device__ __forceinline__ float best_init() { return LOGITS ? -INFINITY : 0.0f; }
 
 __device__ __forceinline__ uint32_t sortable_key(float f) {       // larger float <=> larger key (NaN-free input)
   uint32_t b = __float_as_uint(f);
@@ -104,13 +90,14 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 template <int P, bool LOGITS, int R, bool MT, bool EDGE>
 __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base, size_t plane, int c_begin, int c_end,
                                                  int H, int W, int r0, int x0, int lane, bool col_ok,
-                                                 float (&best)[R][4], int (&lab)[R][4]) {
+                                                 float (&best)[R][4]) {
   constexpr int ROWS = R + 2 * P;
   constexpr int PH = (P > 0) ? P : 1;
   const float NEG = -INFINITY;
   bool row_ok[ROWS];
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) { int r = r0 - P + j; row_ok[j] = !EDGE || (r >= 0 && r < H); }
+  const float edge_l = (lane == 0) ? NEG : 0.0f, edge_r = (lane == 31) ? NEG : 0.0f;
 
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
@@ -122,9 +109,16 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
       else      v[j] = ld_stream4(pl + (long long)j * W);
     }
     if (LOGITS) {
+      // saturation clamp (see kSatLogit) only when some logit of this warp's rows reaches it - rare in practice
+      float4 t4 = v[0];
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j)
-        v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
+      for (int j = 1; j < ROWS; ++j) t4 = max4(t4, v[j]);
+      const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
+      if (__any_sync(0xffffffffu, tmax >= kSatLogit)) {
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+          v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
+      }
     }
     // Halo columns of neighbouring column tiles (rows wider than one 128-column warp tile).  The neighbour shuffles
     // below are rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the
@@ -172,7 +166,7 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
           if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
           float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
           float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
-          if constexpr (!MT) { fl = (lane == 0) ? NEG : fl; fr = (lane == 31) ? NEG : fr; }
+          if constexpr (!MT) { fl += edge_l; fr += edge_r; }      // -inf beyond the row ends (FADD: keeps the ALU pipe free)
           e[P - 1 - q] = fl;
           e[P + 4 + q] = fr;
         }
@@ -183,7 +177,7 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
         float m = e[j];
 #pragma unroll
         for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[j + q]);
-        update_cand<LOGITS>(best[i][j], lab[i][j], ctr[j], m, c);
+        masked_max<LOGITS>(best[i][j], ctr[j], m);
       }
     }
   }
@@ -204,8 +198,8 @@ __device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int P, bool LOGITS, int R, int G, bool MT>
-__global__ void __launch_bounds__(G * 32, (G == 4) ? 7 : 8)
-peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, uint16_t* __restrict__ clabel,
+__global__ void __launch_bounds__(G * 32, (G == 4) ? 8 : 8)
+peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uint8_t* __restrict__ cgroup,
                   unsigned int* __restrict__ hist, int C, int H, int W) {
   const int lane = threadIdx.x & 31;
   const int g = threadIdx.x >> 5;
@@ -219,56 +213,45 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cscore, ui
   const int c_end = min(C, c_begin + cg);
 
   float best[R][4];
-  int lab[R][4];
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { best[i][j] = -INFINITY; lab[i][j] = 0; }
+    for (int j = 0; j < 4; ++j) best[i][j] = best_init<LOGITS>();
 
   const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
   const bool interior = (r0 - P >= 0) && (r0 + R + P <= H) && ((int)(blockIdx.x + 1) * kTW <= W);   // block-uniform
-  constexpr int kMergeBytes = G * R * kTW * 6;
-  __shared__ __align__(128) unsigned char s_raw[kMergeBytes];
-  if (interior) peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
-  else          peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best, lab);
+  if (interior) peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best);
+  else          peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best);
 
-  // merge the G class groups (in class order) through shared memory, then emit one candidate per pixel
-  float (*s_v)[R][kTW] = reinterpret_cast<float (*)[R][kTW]>(s_raw);
-  uint16_t (*s_l)[R][kTW] = reinterpret_cast<uint16_t (*)[R][kTW]>(s_raw + G * R * kTW * 4);
+  // merge the G class groups through shared memory (a plain max), then emit one candidate per pixel
+  __shared__ __align__(16) float s_v[G][R][kTW];
   if (G > 1) {
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
+    for (int i = 0; i < R; ++i)
       *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
-      *reinterpret_cast<ushort4*>(&s_l[g][i][lane * 4]) =
-          make_ushort4((uint16_t)lab[i][0], (uint16_t)lab[i][1], (uint16_t)lab[i][2], (uint16_t)lab[i][3]);
-    }
     __syncthreads();
   }
   for (int i = g; i < R; i += G) {          // warp g finishes rows g, g+G, ...
     int r = r0 + i;
     if (r >= H || !col_ok) continue;
-    float sc[4];
-    int lb[4];
+    float bv[4];
+    uint32_t grp = 0;                        // which class group attained the maximum (first group on ties), 8 bits per pixel
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float bv; int bl;
       if (G > 1) {
-        bv = s_v[0][i][lane * 4 + j]; bl = s_l[0][i][lane * 4 + j];
+        bv[j] = s_v[0][i][lane * 4 + j];
 #pragma unroll
-        for (int gg = 1; gg < G; ++gg) {    // later groups hold later classes: strict > keeps the first maximal class
-          float ov = s_v[gg][i][lane * 4 + j];
-          if (ov > bv) { bv = ov; bl = s_l[gg][i][lane * 4 + j]; }
+        for (int gg = 1; gg < G; ++gg) {
+          const float ov = s_v[gg][i][lane * 4 + j];
+          if (ov > bv[j]) { bv[j] = ov; grp = (grp & ~(0xffu << (8 * j))) | ((uint32_t)gg << (8 * j)); }
         }
       } else {
-        bv = best[i][j]; bl = lab[i][j];
+        bv[j] = best[i][j];
       }
-      finish_cand<LOGITS>(bv, bl, sc[j], lb[j]);
-      atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(sc[j]) >> kHistShift), 1u);
+      atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(bv[j]) >> kHistShift), 1u);
     }
-    size_t o = (size_t)n * plane + (size_t)r * W + x0;
-    *reinterpret_cast<float4*>(cscore + o) = make_float4(sc[0], sc[1], sc[2], sc[3]);
-    ushort4 l4 = make_ushort4((uint16_t)lb[0], (uint16_t)lb[1], (uint16_t)lb[2], (uint16_t)lb[3]);
-    *reinterpret_cast<ushort4*>(clabel + o) = l4;
+    *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + x0) = grp;
+    *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + x0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
   }
 }
 
@@ -285,8 +268,8 @@ constexpr int kTmaClasses = 4;       // classes per stage = warps per CTA
 
 template <bool LOGITS>
 __global__ void __launch_bounds__(128, 7)
-peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __restrict__ heat, float* __restrict__ cscore,
-                 uint16_t* __restrict__ clabel, unsigned int* __restrict__ hist, int C, int H, int W) {
+peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __restrict__ heat, float* __restrict__ cbest,
+                 uint8_t* __restrict__ cgroup, unsigned int* __restrict__ hist, int C, int H, int W) {
   constexpr int P = 1, R = 4, G = 4, ROWS = R + 2 * P;
   constexpr int kStageFloats = kTmaClasses * ROWS * kTW;             // 3072 floats = 12 KB
   __shared__ __align__(128) float s_ring[kTmaStages * kStageFloats];
@@ -299,13 +282,13 @@ peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __re
   const int x0 = lane * 4;
   const size_t plane = (size_t)H * W;
   const float NEG = -INFINITY;
+  const float edge_l = (lane == 0) ? NEG : 0.0f, edge_r = (lane == 31) ? NEG : 0.0f;
 
   float best[R][4];
-  int lab[R][4];
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { best[i][j] = NEG; lab[i][j] = 0; }
+    for (int j = 0; j < 4; ++j) best[i][j] = best_init<LOGITS>();
 
   const bool interior = (r0 - P >= 0) && (r0 + R + P <= H);          // block-uniform
   if (interior) {
@@ -333,7 +316,6 @@ peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __re
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
       const int s2 = it % kTmaStages;
-      const int c = it * kTmaClasses + g;
       ring_wait(&s_full[s2], (it / kTmaStages) & 1);
       const float* st = s_ring + s2 * kStageFloats + g * ROWS * kTW + lane * 4;
       float4 v[ROWS];
@@ -364,54 +346,42 @@ peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __re
       for (int i = 0; i < R; ++i) {
         float fl = __shfl_sync(0xffffffffu, vm[i].w, (lane + 31) & 31);
         float fr = __shfl_sync(0xffffffffu, vm[i].x, (lane + 1) & 31);
-        fl = (lane == 0) ? NEG : fl;
-        fr = (lane == 31) ? NEG : fr;
+        fl += edge_l;
+        fr += edge_r;
         const float e[6] = {fl, vm[i].x, vm[i].y, vm[i].z, vm[i].w, fr};
         const float ctr[4] = {v[i + 1].x, v[i + 1].y, v[i + 1].z, v[i + 1].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) update_cand<LOGITS>(best[i][j], lab[i][j], ctr[j], fmaxf(fmaxf(e[j], e[j + 1]), e[j + 2]), c);
+        for (int j = 0; j < 4; ++j) masked_max<LOGITS>(best[i][j], ctr[j], fmaxf(fmaxf(e[j], e[j + 1]), e[j + 2]));
       }
     }
   } else {
     const int cg = (C + G - 1) / G;
     const int c_begin = g * cg, c_end = min(C, c_begin + cg);
     const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
-    peaks_class_loop<P, LOGITS, R, false, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, true, best, lab);
+    peaks_class_loop<P, LOGITS, R, false, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, true, best);
   }
 
-  // merge the 4 warps' winners: maximal value, lowest class on ties (= first maximal class of torch.max)
-  __syncthreads();                                                   // ring no longer in use: alias it
+  // merge the 4 warps' maxima through shared memory (aliases the ring)
+  __syncthreads();
   float (*s_v)[R][kTW] = reinterpret_cast<float (*)[R][kTW]>(s_ring);
-  uint16_t (*s_l)[R][kTW] = reinterpret_cast<uint16_t (*)[R][kTW]>(s_ring + G * R * kTW);
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
+  for (int i = 0; i < R; ++i)
     *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
-    *reinterpret_cast<ushort4*>(&s_l[g][i][lane * 4]) =
-        make_ushort4((uint16_t)lab[i][0], (uint16_t)lab[i][1], (uint16_t)lab[i][2], (uint16_t)lab[i][3]);
-  }
   __syncthreads();
   {
     const int i = g;                                                 // warp g finishes row g (R == G)
     const int r = r0 + i;
     if (r < H) {
-      float sc[4];
-      int lb[4];
+      float bv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float bv = s_v[0][i][lane * 4 + j];
-        int bl = s_l[0][i][lane * 4 + j];
+        bv[j] = s_v[0][i][lane * 4 + j];
 #pragma unroll
-        for (int gg = 1; gg < G; ++gg) {
-          const float ov = s_v[gg][i][lane * 4 + j];
-          const int ol = s_l[gg][i][lane * 4 + j];
-          if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-        }
-        finish_cand<LOGITS>(bv, bl, sc[j], lb[j]);
-        atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(sc[j]) >> kHistShift), 1u);
+        for (int gg = 1; gg < G; ++gg) bv[j] = fmaxf(bv[j], s_v[gg][i][lane * 4 + j]);
+        atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(bv[j]) >> kHistShift), 1u);
       }
-      const size_t o = (size_t)n * plane + (size_t)r * W + x0;
-      *reinterpret_cast<float4*>(cscore + o) = make_float4(sc[0], sc[1], sc[2], sc[3]);
-      *reinterpret_cast<ushort4*>(clabel + o) = make_ushort4((uint16_t)lb[0], (uint16_t)lb[1], (uint16_t)lb[2], (uint16_t)lb[3]);
+      *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + x0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + x0) = 0xffffffffu;   // classes interleaved: scan all
     }
   }
 }
@@ -421,7 +391,7 @@ peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __re
 // ------------------------------------------------------------------------------------------------------------
 template <bool LOGITS>
 __global__ void __launch_bounds__(256)
-peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cscore, uint16_t* __restrict__ clabel,
+peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uint8_t* __restrict__ cgroup,
                      unsigned int* __restrict__ hist, int C, int H, int W, int P) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -429,8 +399,7 @@ peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cscore,
   if (x >= W || y >= H) return;
   const size_t plane = (size_t)H * W;
   const float* img = heat + (size_t)n * C * plane;
-  float best = -INFINITY;
-  int lab = 0;
+  float best = best_init<LOGITS>();
   const int y_lo = max(0, y - P), y_hi = min(H - 1, y + P);
   const int x_lo = max(0, x - P), x_hi = min(W - 1, x + P);
   for (int c = 0; c < C; ++c) {
@@ -440,14 +409,11 @@ peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cscore,
     for (int yy = y_lo; yy <= y_hi; ++yy)
       for (int xx = x_lo; xx <= x_hi; ++xx) m = fmaxf(m, __ldg(pl + (size_t)yy * W + xx));
     if (LOGITS) { ctr = fminf(ctr, kSatLogit); m = fminf(m, kSatLogit); }
-    update_cand<LOGITS>(best, lab, ctr, m, c);
+    masked_max<LOGITS>(best, ctr, m);
   }
-  float score; int label;
-  finish_cand<LOGITS>(best, lab, score, label);
-  size_t o = (size_t)n * plane + (size_t)y * W + x;
-  cscore[o] = score;
-  clabel[o] = (uint16_t)label;
-  atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(score) >> kHistShift), 1u);
+  cbest[(size_t)n * plane + (size_t)y * W + x] = best;
+  cgroup[(size_t)n * plane + (size_t)y * W + x] = 0xff;
+  atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(best) >> kHistShift), 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -463,7 +429,8 @@ constexpr int kMaxK = 1024;
 constexpr int kListCap = 2048;
 constexpr int kBins = 2048;
 constexpr int kSubShift = kHistShift - 11;   // second-level digit: the next 11 key bits
-constexpr int kRefineAbove = 256;            // sort directly when bin_k-and-above holds at most this many
+constexpr int kRefineAbove = 256;
+constexpr int kLabelBatch = 3;               // classes per lane and batch in the label recovery (8 lanes x 3 = 24 classes at once)            // sort directly when bin_k-and-above holds at most this many
 
 // inclusive block scan over kSelThreads ints (warp shuffles + one smem hop)
 __device__ __forceinline__ int block_inclusive_scan(int v, int* s_warp /*[32]*/) {
@@ -541,7 +508,9 @@ __global__ void sigmoid_kernel(const float* __restrict__ in, float* __restrict__
 }
 
 struct DecodeParams {
-  const float* cscore; const uint16_t* clabel; const unsigned int* hist;
+  const float* cscore; const unsigned int* hist;     // per-pixel best masked value (logit or probability) + its histogram
+  const float* heat; int C, P, from_logits;          // the head map itself: labels are recovered for the k winners only
+  const uint8_t* cgroup; int group_classes;          // class group (of group_classes classes) that holds the winner; 255 = unknown
   const float* box; const float* reid;
   int H, W, E, k;
   int normalize, box_log; float mult; float stride_f;
@@ -612,6 +581,25 @@ __device__ void radix_select_fallback(const float* sc, int HW, int k, unsigned l
   __syncthreads();
 }
 
+// descending bitonic sort of n (power of two) 64-bit keys in shared memory; `pay` (optional) is permuted alongside
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, uint32_t* pay, int n, int tid) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (n >> 1); t += kSelThreads) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b; keys[hi] = a;
+          if (pay != nullptr) { uint32_t t2 = pay[lo]; pay[lo] = pay[hi]; pay[hi] = t2; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // CACHE: H*W <= 16384 and a multiple of 4 - every thread keeps its 16 candidates in registers (loaded once, before
 // the histogram scan, so the L2 latency hides behind it); otherwise the passes re-read the candidate map from L2.
 template <bool CACHE>
@@ -640,27 +628,42 @@ select_gather_kernel(DecodeParams p) {
       cache[q] = (i < n_vec) ? sc4[i] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);   // -inf sorts below every candidate
     }
   }
-  // visit(f): f(key, flat_index) for every candidate of this thread
+  // visit(f): f(key, flat_index, valid) for every candidate of this thread, called the SAME number of times by every
+  // thread of the CTA (valid = false pads the tail) so that f may use warp collectives
   auto visit = [&](auto&& f) {
     if (CACHE) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = tid + q * kSelThreads;
-        if (i < n_vec) {
-          const float fv[4] = {cache[q].x, cache[q].y, cache[q].z, cache[q].w};
+        const float fv[4] = {cache[q].x, cache[q].y, cache[q].z, cache[q].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j);
-        }
+        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec);
       }
     } else {
-      for (int i = tid; i < n_vec; i += kSelThreads) {
-        const float4 v4 = sc4[i];
+      for (int i0 = 0; i0 < n_vec; i0 += kSelThreads) {
+        const int i = i0 + tid;
+        const bool ok = i < n_vec;
+        const float4 v4 = ok ? sc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         const float fv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j);
+        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, ok);
       }
-      for (int i = 4 * n_vec + tid; i < HW; i += kSelThreads) f(sortable_key(sc[i]), i);
+      for (int i0 = 4 * n_vec; i0 < HW; i0 += kSelThreads) {
+        const int i = i0 + tid;
+        const bool ok = i < HW;
+        f(sortable_key(ok ? sc[i] : 0.f), i, ok);
+      }
     }
+  };
+  // warp-aggregated append to s_list: one shared-memory atomic per warp and step instead of one per element
+  auto append = [&](bool pred, unsigned long long entry) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = tid & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&s_n, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) s_list[base + __popc(m & ((1u << lane) - 1u))] = entry;
   };
 
   // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
@@ -684,9 +687,7 @@ select_gather_kernel(DecodeParams p) {
   bool done = false;
   if (n_in_or_above <= kRefineAbove) {
     // few enough: collect every candidate in bin_k or above and sort them all
-    visit([&](uint32_t u, int i) {
-      if ((u >> kHistShift) >= bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
-    });
+    visit([&](uint32_t u, int i, bool ok) { append(ok && (u >> kHistShift) >= bin_k, pack_entry(u, i)); });
     n_sort = n_in_or_above;
     done = true;
   } else {
@@ -695,10 +696,10 @@ select_gather_kernel(DecodeParams p) {
     // of bin_k at or above the sub-bin that holds the k-th largest.
     for (int i = tid; i < kBins; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
-    visit([&](uint32_t u, int i) {
+    visit([&](uint32_t u, int i, bool ok) {
       const uint32_t b = u >> kHistShift;
-      if (b > bin_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
-      else if (b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
+      append(ok && b > bin_k, pack_entry(u, i));
+      if (ok && b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
     });
     __syncthreads();
     const int n_above = s_n;                         // < k by construction
@@ -715,8 +716,8 @@ select_gather_kernel(DecodeParams p) {
     const uint32_t sub_k = (uint32_t)s_scalars[0];
     const int n_total = n_above + s_scalars[1];
     if (n_total <= kListCap) {
-      visit([&](uint32_t u, int i) {
-        if ((u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k) s_list[atomicAdd(&s_n, 1)] = pack_entry(u, i);
+      visit([&](uint32_t u, int i, bool ok) {
+        append(ok && (u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k, pack_entry(u, i));
       });
       n_sort = n_total;
       done = true;
@@ -734,28 +735,102 @@ select_gather_kernel(DecodeParams p) {
   __syncthreads();
 
   // ---- bitonic sort, descending ---------------------------------------------------------------------------
-  for (int size = 2; size <= kp; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (kp >> 1); t += kSelThreads) {
-        int lo = 2 * t - (t & (stride - 1));
-        int hi = lo + stride;
-        bool desc = ((lo & size) == 0);
-        unsigned long long a = s_list[lo], b = s_list[hi];
-        if ((a < b) == desc) { s_list[lo] = b; s_list[hi] = a; }
-      }
-      __syncthreads();
+  bitonic_sort_desc(s_list, nullptr, kp, tid);
+
+  // ---- label recovery + score for the k winners ---------------------------------------------------------------
+  // Reference: labels = argmax over classes of the MASKED map (first maximal class).  For a winner with best value v
+  // that is the first class c with value(c) == v that is a kxk peak.  8 lanes share one winner: each loads C/8
+  // classes (independent loads, one latency round trip); a second look at the 3x3 window is needed only when
+  // several classes hold exactly the same value.
+  __shared__ uint32_t s_label[kMaxK];
+  const size_t plane = (size_t)HW;
+  const float* img = p.heat + (size_t)n * p.C * plane;
+  const int sub = tid & 7;
+  const int scan_len = (p.group_classes > 0) ? p.group_classes : p.C;       // classes to re-read per winner (CTA-uniform)
+  for (int j0 = 0; j0 < k; j0 += kSelThreads / 8) {
+    const int j = j0 + (tid >> 3);
+    const bool act = j < k;
+    int idx = 0;
+    float v = 0.f;
+    if (act) {
+      const unsigned long long w = s_list[j];
+      idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
+      v = key_to_float((uint32_t)(w >> 32));
     }
+    int first = 0x7fffffff;
+    const bool trivial = p.from_logits ? (v == -INFINITY) : (v == 0.0f);     // all-zero column: argmax is class 0
+    // kernel 1 recorded which class group attained the maximum: only those classes are re-read (the C planes of one
+    // pixel are 4*H*W bytes apart - same DRAM bank - so every class read costs a row activation)
+    int c_lo = 0, c_hi = p.C;
+    if (act) {
+      const int gid = p.cgroup[(size_t)n * HW + idx];
+      if (gid != 0xff) { c_lo = gid * p.group_classes; c_hi = min(p.C, c_lo + p.group_classes); }
+    }
+    const bool multi_batch = scan_len > 8 * kLabelBatch;
+    for (int off = 0; off < scan_len; off += 8 * kLabelBatch) {              // uniform trip count for the whole CTA
+      float xv[kLabelBatch];
+      int nmatch = 0;
+#pragma unroll
+      for (int q = 0; q < kLabelBatch; ++q) {                                 // batch the loads: one latency round trip
+        const int c = c_lo + off + sub + 8 * q;
+        xv[q] = (act && !trivial && c < c_hi) ? __ldg(img + (size_t)c * plane + idx) : NAN;
+      }
+#pragma unroll
+      for (int q = 0; q < kLabelBatch; ++q) {
+        if (p.from_logits) xv[q] = fminf(xv[q], kSatLogit);                  // (padding lanes are excluded by the c < c_hi test)
+        const int c = c_lo + off + sub + 8 * q;
+        nmatch += (act && !trivial && c < c_hi && xv[q] == v) ? 1 : 0;
+      }
+      int total = nmatch;                                                     // matches among the 8 lanes of this winner
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+#pragma unroll
+      for (int q = 0; q < kLabelBatch; ++q) {
+        const int c = c_lo + off + sub + 8 * q;
+        if (!(act && !trivial && c < c_hi && xv[q] == v) || c >= first) continue;
+        bool peak = true;                                                     // a unique match IS the peak that produced v
+        if (total > 1 || multi_batch) {
+          const int y = idx / p.W, xx0 = idx - y * p.W;
+          float m = xv[q];
+          for (int yy = max(0, y - p.P); yy <= min(p.H - 1, y + p.P); ++yy)
+            for (int xx = max(0, xx0 - p.P); xx <= min(p.W - 1, xx0 + p.P); ++xx) {
+              float t = __ldg(img + (size_t)c * plane + (size_t)yy * p.W + xx);
+              if (p.from_logits) t = fminf(t, kSatLogit);
+              m = fmaxf(m, t);
+            }
+          peak = (m == xv[q]);
+        }
+        if (peak) first = c;
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (act && sub == 0) {
+      float score = p.from_logits ? sigmoid32(v) : v;
+      uint32_t label = (first == 0x7fffffff) ? 0u : (uint32_t)first;
+      if (score == 0.0f) label = 0u;                       // underflowed / zero candidates arg-max to class 0
+      s_label[j] = label;
+      // canonical output order is (score desc, index asc): distinct logits can round to one probability, so re-key
+      s_list[j] = pack_entry(sortable_key(score), idx);
+    }
+  }
+  __syncthreads();
+  if (p.from_logits) {
+    int kq = 1;
+    while (kq < k) kq <<= 1;
+    for (int i = k + tid; i < kq; i += kSelThreads) { s_list[i] = 0ull; }
+    __syncthreads();
+    bitonic_sort_desc(s_list, s_label, kq, tid);
   }
 
   // ---- gather + decode -------------------------------------------------------------------------------------
-  const size_t plane = (size_t)HW;
   for (int j = tid; j < k; j += kSelThreads) {
     unsigned long long w = s_list[j];
     int idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
     size_t o = (size_t)n * k + j;
     p.scores[o] = key_to_float((uint32_t)(w >> 32));
     p.indices[o] = idx;
-    p.labels[o] = p.clabel[(size_t)n * HW + idx];
+    p.labels[o] = (long long)s_label[j];
     if (p.box == nullptr) continue;
     float4 b4 = decode_box(p.box + (size_t)n * 4 * plane, plane, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
     *reinterpret_cast<float4*>(p.boxes + o * 4) = b4;
@@ -774,20 +849,22 @@ select_gather_kernel(DecodeParams p) {
 // Host side
 // ------------------------------------------------------------------------------------------------------------
 template <int P, bool LOGITS>
-static void launch_fast(const float* heat, float* cscore, uint16_t* clabel, unsigned int* hist, int N, int C, int H, int W,
-                        cudaStream_t st) {
+static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+                       cudaStream_t st) {
   constexpr int R = 4;
   dim3 grid((W + kTW - 1) / kTW, (H + R - 1) / R, N);
   const bool mt = grid.x > 1;        // rows wider than one 128-column warp tile need halo columns from neighbours
 #define CNL_LAUNCH_PEAKS(G_)                                                                                      \
   do {                                                                                                            \
-    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W);  \
-    else    peaks_fast_kernel<P, LOGITS, R, G_, false><<<grid, G_ * 32, 0, st>>>(heat, cscore, clabel, hist, C, H, W); \
+    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W);  \
+    else    peaks_fast_kernel<P, LOGITS, R, G_, false><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W); \
   } while (0)
-  if (C >= 32) CNL_LAUNCH_PEAKS(4);
-  else if (C >= 2) CNL_LAUNCH_PEAKS(2);
+  int groups = 1;
+  if (C >= 32) { CNL_LAUNCH_PEAKS(4); groups = 4; }
+  else if (C >= 2) { CNL_LAUNCH_PEAKS(2); groups = 2; }
   else CNL_LAUNCH_PEAKS(1);
 #undef CNL_LAUNCH_PEAKS
+  return (C + groups - 1) / groups;          // classes per group, for the label recovery
 }
 
 typedef CUresult (*EncodeTiledFnD)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -811,9 +888,10 @@ static bool make_heat_map(CUtensorMap* m, const float* heat, int N, int C, int H
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// returns the number of classes per recorded class group (0 = no group information, scan every class)
 template <bool LOGITS>
-static void launch_peaks(const float* heat, float* cscore, uint16_t* clabel, unsigned int* hist, int N, int C, int H, int W,
-                         int P, bool force_generic, cudaStream_t st) {
+static int launch_peaks(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+                        int P, bool force_generic, cudaStream_t st) {
   // CNL_PEAKS_TMA=1 selects the TMA-fed kernel (measured 50 us vs 43 us for the register-prefetch kernel at
   // 32x80x128x128 on B200: the pass is bounded by the 1.5x halo re-reads at L2, not by bytes in flight; kept for tuning).
   static const int use_tma = (getenv("CNL_PEAKS_TMA") && atoi(getenv("CNL_PEAKS_TMA")) != 0) ? 1 : 0;
@@ -822,20 +900,21 @@ static void launch_peaks(const float* heat, float* cscore, uint16_t* clabel, uns
     CUtensorMap m;
     if (make_heat_map(&m, heat, N, C, H, W)) {
       dim3 grid(1, H / 4, N);
-      peaks_tma_kernel<LOGITS><<<grid, 128, 0, st>>>(m, heat, cscore, clabel, hist, C, H, W);
-      return;
+      peaks_tma_kernel<LOGITS><<<grid, 128, 0, st>>>(m, heat, cscore, cgroup, hist, C, H, W);
+      return 0;
     }
   }
   bool fast = !force_generic && (W % 4 == 0) && P <= 2 && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   if (fast) {
     switch (P) {
-      case 0: launch_fast<0, LOGITS>(heat, cscore, clabel, hist, N, C, H, W, st); return;
-      case 1: launch_fast<1, LOGITS>(heat, cscore, clabel, hist, N, C, H, W, st); return;
-      case 2: launch_fast<2, LOGITS>(heat, cscore, clabel, hist, N, C, H, W, st); return;
+      case 0: return launch_fast<0, LOGITS>(heat, cscore, cgroup, hist, N, C, H, W, st);
+      case 1: return launch_fast<1, LOGITS>(heat, cscore, cgroup, hist, N, C, H, W, st);
+      case 2: return launch_fast<2, LOGITS>(heat, cscore, cgroup, hist, N, C, H, W, st);
     }
   }
   dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-  peaks_generic_kernel<LOGITS><<<grid, 256, 0, st>>>(heat, cscore, clabel, hist, C, H, W, P);
+  peaks_generic_kernel<LOGITS><<<grid, 256, 0, st>>>(heat, cscore, cgroup, hist, C, H, W, P);
+  return 0;
 }
 
 static size_t hist_bytes(int n) { return align_up((size_t)n * kHistBins * sizeof(unsigned int), 256); }
@@ -853,7 +932,7 @@ int cnl_compiled_sm(void) { return 100; }
 
 size_t cnl_decode_workspace_bytes(int n, int h, int w) {
   if (n <= 0 || h <= 0 || w <= 0) return 0;
-  return hist_bytes(n) + score_bytes(n, h, w) + align_up((size_t)n * h * w * sizeof(uint16_t), 256);
+  return hist_bytes(n) + score_bytes(n, h, w) + align_up((size_t)n * h * w, 256);
 }
 
 int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
@@ -893,15 +972,17 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned int* hist = static_cast<unsigned int*>(workspace);
   float* cscore = reinterpret_cast<float*>(static_cast<char*>(workspace) + hist_bytes(n));
-  uint16_t* clabel = reinterpret_cast<uint16_t*>(static_cast<char*>(workspace) + hist_bytes(n) + score_bytes(n, h, w));
   const int P = (nms_kernel - 1) / 2;
   CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
-  if (from_logits) launch_peaks<true>(heatmap, cscore, clabel, hist, n, c, h, w, P, force_generic, st);
-  else             launch_peaks<false>(heatmap, cscore, clabel, hist, n, c, h, w, P, force_generic, st);
+  uint8_t* cgroup = reinterpret_cast<uint8_t*>(static_cast<char*>(workspace) + hist_bytes(n) + score_bytes(n, h, w));
+  const int group_classes = from_logits ? launch_peaks<true>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st)
+                                        : launch_peaks<false>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st);
   CNL_CUDA_CHECK(cudaGetLastError());
 
   DecodeParams p;
-  p.cscore = cscore; p.clabel = clabel; p.hist = hist; p.box = box_offsets; p.reid = reid;
+  p.cscore = cscore; p.hist = hist; p.box = box_offsets; p.reid = reid;
+  p.heat = heatmap; p.C = c; p.P = P; p.from_logits = from_logits ? 1 : 0;
+  p.cgroup = cgroup; p.group_classes = group_classes;
   p.H = h; p.W = w; p.E = reid_dim; p.k = num_detections;
   p.normalize = normalize_boxes; p.box_log = box_log; p.mult = box_multiplier; p.stride_f = (float)stride;
   p.boxes = boxes; p.scores = scores; p.labels = reinterpret_cast<long long*>(labels);
