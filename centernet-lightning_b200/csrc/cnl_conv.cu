@@ -515,6 +515,7 @@ struct OpInfo {
   cnl_conv_desc d;
   // conv
   int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster;
+  bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
   std::vector<__half> w_packed;       // [plane][tap][cout_pad][cin]
@@ -618,6 +619,9 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / stage_bytes);
   if (op.num_stages < 2) return fail(CNL_ERR_UNSUPPORTED, "conv tile does not fit shared memory");
   op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
+  // The separate correction accumulator pays off where the reduction is long (its rounding bias grows with the number
+  // of accumulate steps); short reductions (K < 576: stem, 1x1 convs) keep the double-buffered single one.
+  op.corr = (d.ksize * d.ksize * (d.cin / 64)) >= 9;
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = d.ksize * d.ksize;
@@ -669,6 +673,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - 4 * planes * kStageWarpBytes) / stage_bytes);
   op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
+  op.corr = false;                         // K = 256
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
@@ -852,7 +857,8 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (e->precision == CNL_PRECISION_SPLIT)            return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true>, op.src_map, op.w_map, op.dst_map, p);
+    if (e->precision == CNL_PRECISION_SPLIT && op.corr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true>, op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT)       return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false>, op.src_map, op.w_map, op.dst_map, p);
     else if (e->precision == CNL_PRECISION_SPLIT_FUSED) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false>, op.src_map, op.w_map, op.dst_map, p);
     return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, op.src_map, op.w_map, op.dst_map, p);
   };

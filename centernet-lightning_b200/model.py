@@ -109,9 +109,10 @@ class EngineModel(nn.Module):
     """Stands where the reference's GenericModel stands (``CenterNet.model``): same parameters, same call contract
     ``model(images) -> Dict[str, Tensor]`` of raw head outputs, executed by the sm_100a engine."""
 
-    def __init__(self, backbone: _Backbone, neck: _FPN, heads: nn.Module, precision: int):
+    def __init__(self, backbone: _Backbone, neck: _FPN, heads: nn.Module, precision: int, backbone_name: str = "resnet34"):
         super().__init__()
         self.backbone, self.neck, self.heads = backbone, neck, heads
+        self.backbone_name = backbone_name
         self.precision = precision
         self._engines: Dict[Tuple, Engine] = {}
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
@@ -132,7 +133,7 @@ class EngineModel(nn.Module):
         if eng is None:
             names = self.head_names()
             depth = getattr(self.heads, names[0]).depth
-            plan = build_plan(self.state_dict(), head_names=names, head_depth=depth)
+            plan = build_plan(self.state_dict(), backbone=self.backbone_name, head_names=names, head_depth=depth)
             eng = Engine(plan, n, h, w, images.device, precision=self.precision)
             self._engines[key] = eng
         return eng
@@ -178,7 +179,7 @@ class CenterNet(nn.Module):
         heads.add_module("box_2d", _Head(c, 4, init_bias=box_init_bias, **head_config))
         if reid_dim:
             heads.add_module("reid", _Head(c, reid_dim, **head_config))
-        self.model = EngineModel(bb, nk, heads, _PRECISIONS[precision])
+        self.model = EngineModel(bb, nk, heads, _PRECISIONS[precision], backbone)
         self.stride = bb.stride // nk.stride                                   # reference models/meta.py:96
         self.num_classes = num_classes
         self._graphs: Dict[Tuple, Any] = {}

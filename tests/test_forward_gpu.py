@@ -213,3 +213,22 @@ def test_inference_detection_folder(cuda, tmp_path):
     assert np.all(out["scores"][:, :-1] >= out["scores"][:, 1:])
     one = net.inference_detection(str(tmp_path), img_names=["img_3.png"], batch_size=2, num_detections=20, img_size=128)
     np.testing.assert_allclose(one["scores"][0], out["scores"][3], rtol=0, atol=1e-6)
+
+
+def test_small_variant_resnet18_fpn128_heads128x2(cuda):
+    """The other published variant (reference docs/experiments.md:24: FPN dim 128, heads w128 d2) on a ResNet-18 trunk
+    (reference tests/test_models.py:37 lists resnet18): exercises Cout tiles of 128 and a 2-deep tower."""
+    from centernet_lightning_b200.model import CenterNet
+    cfg = dict(neck_config={"out_channels": 128}, head_config={"width": 128, "depth": 2})
+    spec = spec_model.synth_init(spec_model.build_spec_model(20, backbone="resnet18", **cfg), seed=6)
+    net = CenterNet(20, backbone="resnet18", box_multiplier=16.0, **cfg)
+    net.model.load_state_dict(spec.state_dict())
+    net = net.to(cuda)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((3, 3, 224, 160), generator=g)
+    with torch.no_grad():
+        ref = spec(x)
+    out = net.model(x.to(cuda))
+    for k in ref:
+        assert tuple(out[k].shape) == tuple(ref[k].shape) == (3, ref[k].shape[1], 56, 40)
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=0, atol=TOL, err_msg=k)
