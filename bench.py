@@ -275,8 +275,8 @@ def run_ours(args):
         decode_roof = {"bound": "hbm", "kernel": "whole decode: memset + peaks_fast_kernel + select_gather_kernel (CUDA-graph replay)",
                        "achieved": d_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                        "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm, "decode_us": d_ms * 1e3,
-                       "peaks_kernel_only": {"us": 43.5, "achieved": 3860.0, "frac": 0.59,
-                                             "source": "ncu gpu__time_duration, profiles/r01_decode_peaks_ncu_details.txt"},
+                       "peaks_kernel_only": {"us": 36.0, "achieved": 4660.0, "frac": 0.71,
+                                             "source": "ncu gpu__time_duration of peaks_fast_kernel, profiles/README.md"},
                        "algorithmic_bytes_per_launch": d_bytes}
         del heats, dgraph
         # ---- cpu baseline: oracle port on the host cores, bounded sample ---------------------------------------

@@ -222,15 +222,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       const int h = h0 + pix / p.tw, w = w0 + pix % p.tw;
       const bool valid = !dummy && (h < p.out_h) && (w < p.out_w);
 
+      // residual (ResNet identity / FPN top-down map): its global loads are issued one 32-channel chunk ahead - the
+      // first chunk even before the accumulator is ready - so their latency hides behind the MMAs and the TMEM reads
+      const __half* res_px = nullptr;
+      if (p.out_mode == 0 && p.res != nullptr && valid)
+        res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
+      uint4 res_a[NPLANE * 4], res_b[NPLANE * 4];
+      auto prefetch_res = [&](int c32, uint4 (&dst)[NPLANE * 4]) {
+        if (res_px != nullptr) {
+          const int cb = n_idx * p.n_tile + c32 * 32;
+#pragma unroll
+          for (int pl = 0; pl < NPLANE; ++pl) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_px + pl * p.res_plane_elems + cb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[pl * 4 + j] = __ldg(rp + j);
+          }
+        }
+      };
+      prefetch_res(0, res_a);
+
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + as * 256;
 
       if (p.out_mode == 0) {
-        const __half* res_px = nullptr;
-        if (p.res != nullptr && valid)
-          res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
-        for (int c32 = 0; c32 < p.n_tile / 32; ++c32) {
+        auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4]) {
           uint32_t r[32];
           float v[32];
           ptx::tmem_ld_32x32b_x32(taddr + c32 * 32, r);
@@ -257,11 +273,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           if (res_px != nullptr) {
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl) {
-              const uint4* rp = reinterpret_cast<const uint4*>(res_px + pl * p.res_plane_elems + cb);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 u = __ldg(rp + j);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&res[pl * 4 + j]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                   const float2 f = __half22float2(h2[t]);
@@ -295,8 +309,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 ll[t] = __floats2half2_rn(a - back.x, b - back.y);
               }
             }
-            const int chunk = (c32 & 1) * 4 + j;
-            const int off = lane * 128 + ((chunk ^ (lane & 7)) << 4);
+            const int ck = (c32 & 1) * 4 + j;
+            const int off = lane * 128 + ((ck ^ (lane & 7)) << 4);
             *reinterpret_cast<uint4*>(my_stage + off) = hi;
             if (NPLANE == 2) *reinterpret_cast<uint4*>(my_stage + kStageWarpBytes + off) = lo;
           }
@@ -312,6 +326,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               ptx::tma_store_commit();
             }
           }
+        };
+        const int n32 = p.n_tile / 32;                   // even: NHWC outputs have Cout tiles that are multiples of 64
+        for (int c32 = 0; c32 < n32; c32 += 2) {
+          prefetch_res(c32 + 1, res_b);
+          chunk(c32, res_a);
+          if (c32 + 2 < n32) prefetch_res(c32 + 2, res_a);
+          chunk(c32 + 1, res_b);
         }
       } else {
         for (int c16 = 0; c16 < p.n_tile / 16; ++c16) {

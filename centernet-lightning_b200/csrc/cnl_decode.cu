@@ -500,6 +500,14 @@ __global__ void gather_boxes_kernel(const float* __restrict__ box, const long lo
       decode_box(box + (size_t)n * 4 * plane, plane, (int)idx, H, W, normalize, box_log, mult, stride_f);
 }
 
+// torchvision.ops.box_convert(boxes, 'xyxy', 'xywh') as the reference's validation_step applies it (centernet.py:207)
+__global__ void xyxy_to_xywh_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 b = in[i];
+  out[i] = make_float4(b.x, b.y, __fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
 // Elementwise logistic for the G1 forward() alias (heads return probabilities there): same sigmoid32 as the fused decode.
 __global__ void sigmoid_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -606,7 +614,7 @@ template <bool CACHE>
 __global__ void __launch_bounds__(kSelThreads)
 select_gather_kernel(DecodeParams p) {
   __shared__ unsigned long long s_list[kListCap];
-  __shared__ int s_hist[kBins];
+  __shared__ __align__(8) int s_hist[kBins];
   __shared__ int s_warp[32];
   __shared__ int s_scalars[3];
   __shared__ int s_n;
@@ -743,6 +751,7 @@ select_gather_kernel(DecodeParams p) {
   // classes (independent loads, one latency round trip); a second look at the 3x3 window is needed only when
   // several classes hold exactly the same value.
   __shared__ uint32_t s_label[kMaxK];
+  unsigned long long* s_out = reinterpret_cast<unsigned long long*>(s_hist);   // 8 KB = kMaxK entries; histogram no longer needed
   const size_t plane = (size_t)HW;
   const float* img = p.heat + (size_t)n * p.C * plane;
   const int sub = tid & 7;
@@ -811,21 +820,22 @@ select_gather_kernel(DecodeParams p) {
       if (score == 0.0f) label = 0u;                       // underflowed / zero candidates arg-max to class 0
       s_label[j] = label;
       // canonical output order is (score desc, index asc): distinct logits can round to one probability, so re-key
-      s_list[j] = pack_entry(sortable_key(score), idx);
+      // (into a second list: the first one is still being read by the other lanes of this winner)
+      s_out[j] = pack_entry(sortable_key(score), idx);
     }
   }
   __syncthreads();
   if (p.from_logits) {
     int kq = 1;
     while (kq < k) kq <<= 1;
-    for (int i = k + tid; i < kq; i += kSelThreads) { s_list[i] = 0ull; }
+    for (int i = k + tid; i < kq; i += kSelThreads) { s_out[i] = 0ull; }
     __syncthreads();
-    bitonic_sort_desc(s_list, s_label, kq, tid);
+    bitonic_sort_desc(s_out, s_label, kq, tid);
   }
 
   // ---- gather + decode -------------------------------------------------------------------------------------
   for (int j = tid; j < k; j += kSelThreads) {
-    unsigned long long w = s_list[j];
+    unsigned long long w = s_out[j];
     int idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
     size_t o = (size_t)n * k + j;
     p.scores[o] = key_to_float((uint32_t)(w >> 32));
@@ -839,7 +849,7 @@ select_gather_kernel(DecodeParams p) {
     const int E = p.E;
     for (int t = tid; t < k * E; t += kSelThreads) {
       int j = t / E, e = t - j * E;
-      int idx = (int)(0xffffffffu - (uint32_t)(s_list[j] & 0xffffffffull));
+      int idx = (int)(0xffffffffu - (uint32_t)(s_out[j] & 0xffffffffull));
       p.emb[((size_t)n * k + j) * E + e] = __ldg(p.reid + ((size_t)n * E + e) * plane + idx);
     }
   }
@@ -989,6 +999,17 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   p.indices = reinterpret_cast<long long*>(indices); p.emb = embeddings;
   if ((h * w) % 4 == 0 && h * w <= 4 * 4 * kSelThreads) select_gather_kernel<true><<<n, kSelThreads, 0, st>>>(p);
   else                                                  select_gather_kernel<false><<<n, kSelThreads, 0, st>>>(p);
+  CNL_CUDA_CHECK(cudaGetLastError());
+  return CNL_OK;
+}
+
+int cnl_boxes_xyxy_to_xywh(const float* boxes_xyxy, float* boxes_xywh, size_t n_boxes, void* stream) {
+  if (!boxes_xyxy || !boxes_xywh) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_boxes_xyxy_to_xywh: null pointer argument");
+  if ((reinterpret_cast<uintptr_t>(boxes_xyxy) | reinterpret_cast<uintptr_t>(boxes_xywh)) & 15)
+    return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_boxes_xyxy_to_xywh: boxes must be 16-byte aligned");
+  if (n_boxes == 0) return CNL_OK;
+  xyxy_to_xywh_kernel<<<(unsigned)((n_boxes + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(boxes_xyxy), reinterpret_cast<float4*>(boxes_xywh), n_boxes);
   CNL_CUDA_CHECK(cudaGetLastError());
   return CNL_OK;
 }

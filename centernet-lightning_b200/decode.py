@@ -84,6 +84,19 @@ def decode_into(bufs: DecodeBuffers, heatmap: torch.Tensor, box_offsets: torch.T
     return 3            # memset + peaks + select
 
 
+def boxes_xyxy_to_xywh(boxes: torch.Tensor) -> torch.Tensor:
+    """(...,4) xyxy -> xywh through the library (reference models/centernet.py:207, torchvision box_convert)."""
+    lib = _lib.load()
+    if not boxes.is_cuda or boxes.dtype != torch.float32 or boxes.shape[-1] != 4:
+        raise ValueError("boxes must be a CUDA float32 tensor (...,4)")
+    boxes = boxes.contiguous()
+    out = torch.empty_like(boxes)
+    st = lib.cnl_boxes_xyxy_to_xywh(boxes.data_ptr(), out.data_ptr(), boxes.numel() // 4,
+                                    torch.cuda.current_stream(boxes.device).cuda_stream)
+    _lib.check(st, "cnl_boxes_xyxy_to_xywh")
+    return out
+
+
 def sigmoid(x: torch.Tensor) -> torch.Tensor:
     """fp32 logistic through the library (reference models/centernet.py:205)."""
     lib = _lib.load()

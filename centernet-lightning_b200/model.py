@@ -302,6 +302,17 @@ class CenterNet(nn.Module):
             out_done[(i - 1) & 1].synchronize()
             yield host_out[(i - 1) & 1]
 
+    @torch.no_grad()
+    def predict_step(self, images: torch.Tensor) -> List[Dict[str, Any]]:
+        """The inference half of the reference's validation_step (models/centernet.py:202-209): forward, decode,
+        boxes xyxy -> xywh (COCO format), one dict of numpy arrays per image - ready for CocoEvaluator.update."""
+        det = self.detect(images)
+        boxes = _decode.boxes_xyxy_to_xywh(det["boxes"])
+        host = {"boxes": boxes.cpu().numpy(), "scores": det["scores"].cpu().numpy(), "labels": det["labels"].cpu().numpy()}
+        if "embeddings" in det:
+            host["embeddings"] = det["embeddings"].cpu().numpy()
+        return [{k: v[i] for k, v in host.items()} for i in range(images.shape[0])]
+
     def invalidate(self) -> None:
         self._graphs.clear()
         self.model.invalidate()

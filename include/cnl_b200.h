@@ -71,6 +71,10 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
  * (centernet_lightning/models/centernet.py:205; G1 forward(), tests/test_models.py:88-99). */
 int cnl_sigmoid(const float* in, float* out, size_t n, void* stream);
 
+/* (N*k,4) xyxy -> xywh, the torchvision.ops.box_convert the reference's validation_step applies before handing
+ * detections to the COCO evaluator (centernet_lightning/models/centernet.py:207).  In-place allowed. */
+int cnl_boxes_xyxy_to_xywh(const float* boxes_xyxy, float* boxes_xywh, size_t n_boxes, void* stream);
+
 /* Stand-alone box gather for caller-supplied indices: CenterNet.gather_and_decode_boxes
  * (centernet_lightning/models/centernet.py:263-304, a staticmethod the reference also calls from its
  * loss, :162-165).  indices (N,k) int64 device; boxes (N,k,4) f32, 16-byte aligned.  Out-of-range

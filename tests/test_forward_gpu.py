@@ -232,3 +232,19 @@ def test_small_variant_resnet18_fpn128_heads128x2(cuda):
     for k in ref:
         assert tuple(out[k].shape) == tuple(ref[k].shape) == (3, ref[k].shape[1], 56, 40)
         np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=0, atol=TOL, err_msg=k)
+
+
+def test_predict_step_coco_format(cuda):
+    """reference models/centernet.py:202-209: per-image dicts of numpy arrays, boxes in xywh."""
+    from torchvision.ops import box_convert
+    kw = dict(model=dict(num_classes=80), seed=0, n=2, size=128, img_seed=31)
+    _, net = _build(kw)
+    net = net.to(cuda)
+    x = cases.make_image(kw).to(cuda)
+    det = {k: v.clone().cpu() for k, v in net.detect(x).items()}
+    preds = net.predict_step(x)
+    assert isinstance(preds, list) and len(preds) == 2 and set(preds[0]) == {"boxes", "scores", "labels"}
+    for i, p in enumerate(preds):
+        assert p["boxes"].shape == (100, 4) and p["labels"].dtype == np.int64
+        np.testing.assert_array_equal(p["boxes"], box_convert(det["boxes"][i], "xyxy", "xywh").numpy())
+        np.testing.assert_array_equal(p["scores"], det["scores"][i].numpy())
