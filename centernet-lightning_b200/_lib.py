@@ -8,7 +8,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcnl_b200.so")
+# CNL_LIB points at another build of the SAME library (A/B timing of kernel variants); it is never a fallback
+LIB_PATH = os.environ.get("CNL_LIB") or os.path.join(_HERE, "libcnl_b200.so")
 
 EXPORTS = (
     "cnl_last_error", "cnl_version", "cnl_compiled_sm",

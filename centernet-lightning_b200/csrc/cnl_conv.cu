@@ -39,9 +39,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // 64 fp16 = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 constexpr int kSmemLimit = 232448 - 1024;    // 227 KB opt-in shared memory per CTA minus the static part (barriers)
-constexpr int kStageWarpBytes = 32 * 128;    // epilogue staging: 32 pixels x 64 channels fp16 per warp and plane
+constexpr int kStageWarpBytes = 32 * 64;     // epilogue staging: 32 pixels x 32 channels fp16 per warp and plane
 
 struct ConvParams {
   int n_img, out_h, out_w;
@@ -59,6 +60,8 @@ struct ConvParams {
   int res_up, res_c, res_h, res_w;
   long long res_plane_elems;
   int num_stages;
+  int acc_stages;               // TMEM accumulator stages (2 = the epilogue of tile i overlaps the MMAs of tile i+1)
+  int corr_off;                 // column offset of the correction accumulator inside an accumulator stage (CORR only)
   int store_w, store_h;         // per-warp TMA store box in pixels (store_w * store_h == 32)
   int cluster;                  // CTAs per cluster sharing one multicast weight tile (1 = no cluster)
 };
@@ -67,9 +70,13 @@ struct ConvParams {
 // The implicit-GEMM convolution kernel
 // ------------------------------------------------------------------------------------------------------------
 // CORR = true (CNL_PRECISION_SPLIT): the hi*lo and lo*hi correction products accumulate in their own TMEM accumulator
-// (columns 256..511) and are added to the hi*hi sum in the epilogue.  The tensor core truncates (RZ) after every
-// accumulate step, which biases long sums; keeping the 2^-11-times-smaller correction stream out of the main
-// accumulator cuts the number of roundings at full magnitude by 3x.  It costs the accumulator double buffering.
+// (p.corr_off columns after the main one) and are added to the hi*hi sum in the epilogue.  The tensor core truncates
+// (RZ) after every accumulate step, which biases long sums; keeping the 2^-11-times-smaller correction stream out of
+// the main accumulator cuts the number of roundings at full magnitude by 3x.  With Cout tiles of 256 it costs the
+// accumulator double buffering (512 TMEM columns); narrower tiles keep two stages.
+//
+// Epilogue: 8 warps.  Warps w and w+4 own the same TMEM lane quarter (w & 3) and split the tile's columns in halves,
+// so two tcgen05.ld -> convert -> store chains per scheduler overlap their latencies.
 template <int NPLANE, bool CORR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap w_map,
@@ -87,7 +94,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 
   const int b_tile_bytes = p.n_tile * kBlockK * 2;
   const int stage_bytes = NPLANE * (kATileBytes + b_tile_bytes);
-  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;        // [4 warps][NPLANE][4096], 1024-aligned
+  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;        // [8 warps][NPLANE][2048], 1024-aligned
   const int taps = p.kh * p.kw;
   const int k_iters = taps * p.kblocks;
 
@@ -96,7 +103,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     ptx::prefetch_tmap(&w_map);
     if (p.out_mode == 0) ptx::prefetch_tmap(&dst_map);
     for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], p.cluster); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -119,6 +126,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   const int group0 = blockIdx.x / csize, group_step = gridDim.x / csize;
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const bool two_acc = p.acc_stages == 2;
 
   if (warp == 0) {
     // ===================================== TMA producer ==============================================
@@ -170,12 +178,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       uint32_t phase = 0;
       int acc_it = 0;
       for (int grp = group0; grp < total_groups; grp += group_step, ++acc_it) {
-        const int as = CORR ? 0 : (acc_it & 1);
-        const uint32_t aphase = CORR ? (acc_it & 1) : ((acc_it >> 1) & 1);
+        const int as = two_acc ? (acc_it & 1) : 0;
+        const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
-        const uint32_t d_corr = CORR ? (tmem_base + 256) : d_tmem;
+        const uint32_t d_corr = CORR ? (d_tmem + p.corr_off) : d_tmem;
         for (int it = 0; it < k_iters; ++it) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -202,14 +210,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       }
     }
   } else {
-    // ===================================== epilogue (warps 2..5) =====================================
+    // ===================================== epilogue (warps 2..9) =====================================
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                    // which half of the tile's columns this warp drains
     const int lane_base = q * 32;
     uint8_t* my_stage = staging + (size_t)(warp - 2) * NPLANE * kStageWarpBytes;
     int acc_it = 0;
     for (int grp = group0; grp < total_groups; grp += group_step, ++acc_it) {
-      const int as = CORR ? 0 : (acc_it & 1);
-      const uint32_t aphase = CORR ? (acc_it & 1) : ((acc_it >> 1) & 1);
+      const int as = two_acc ? (acc_it & 1) : 0;
+      const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
       const int n_idx = grp % p.n_tiles;
       int m_idx = (grp / p.n_tiles) * csize + crank;
       int img = m_idx / tiles_per_img;
@@ -221,38 +230,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       const int pix = lane_base + lane;
       const int h = h0 + pix / p.tw, w = w0 + pix % p.tw;
       const bool valid = !dummy && (h < p.out_h) && (w < p.out_w);
-
-      // residual (ResNet identity / FPN top-down map): its global loads are issued one 32-channel chunk ahead - the
-      // first chunk even before the accumulator is ready - so their latency hides behind the MMAs and the TMEM reads
-      const __half* res_px = nullptr;
-      if (p.out_mode == 0 && p.res != nullptr && valid)
-        res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
-      uint4 res_a[NPLANE * 4], res_b[NPLANE * 4];
-      auto prefetch_res = [&](int c32, uint4 (&dst)[NPLANE * 4]) {
-        if (res_px != nullptr) {
-          const int cb = n_idx * p.n_tile + c32 * 32;
-#pragma unroll
-          for (int pl = 0; pl < NPLANE; ++pl) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res_px + pl * p.res_plane_elems + cb);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[pl * 4 + j] = __ldg(rp + j);
-          }
-        }
-      };
-      prefetch_res(0, res_a);
-
-      ptx::mbar_wait(&tmem_full_bar[as], aphase);
-      ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + as * 256;
 
       if (p.out_mode == 0) {
+        const int n32 = p.n_tile / 32;                   // NHWC outputs have Cout tiles that are multiples of 64
+        const int c_lo = half * (n32 / 2), c_hi = c_lo + n32 / 2;
+        // residual (ResNet identity / FPN top-down map): its global loads are issued one 32-channel chunk ahead - the
+        // first chunk even before the accumulator is ready - so their latency hides behind the MMAs and the TMEM reads
+        const __half* res_px = nullptr;
+        if (p.res != nullptr && valid)
+          res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
+        uint4 res_a[NPLANE * 4], res_b[NPLANE * 4];
+        auto prefetch_res = [&](int c32, uint4 (&dst)[NPLANE * 4]) {
+          if (res_px != nullptr) {
+            const int cb = n_idx * p.n_tile + c32 * 32;
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res_px + pl * p.res_plane_elems + cb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[pl * 4 + j] = __ldg(rp + j);
+            }
+          }
+        };
+        prefetch_res(c_lo, res_a);
+
+        ptx::mbar_wait(&tmem_full_bar[as], aphase);
+        ptx::tc_fence_after();
+
         auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4]) {
           uint32_t r[32];
           float v[32];
           ptx::tmem_ld_32x32b_x32(taddr + c32 * 32, r);
           if (CORR) {
             uint32_t rc[32];
-            ptx::tmem_ld_32x32b_x32(taddr + 256 + c32 * 32, rc);
+            ptx::tmem_ld_32x32b_x32(taddr + p.corr_off + c32 * 32, rc);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
@@ -289,13 +300,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
-          if ((c32 & 1) == 0) {
-            // the previous TMA store out of this warp's staging buffers must have finished reading them
-            if (lane == 0) ptx::tma_store_wait_read<0>();
-            __syncwarp();
-          }
+          // the previous TMA store out of this warp's staging buffers must have finished reading them
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                  // 8 channels = one 16-byte chunk, XOR-swizzled by row
+          for (int j = 0; j < 4; ++j) {                  // 8 channels = one 16-byte chunk; rows are 64 B, SWIZZLE_64B
             uint4 hi, lo;
             __half2* hh = reinterpret_cast<__half2*>(&hi);
             __half2* ll = reinterpret_cast<__half2*>(&lo);
@@ -309,39 +318,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                 ll[t] = __floats2half2_rn(a - back.x, b - back.y);
               }
             }
-            const int ck = (c32 & 1) * 4 + j;
-            const int off = lane * 128 + ((ck ^ (lane & 7)) << 4);
+            const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(my_stage + off) = hi;
             if (NPLANE == 2) *reinterpret_cast<uint4*>(my_stage + kStageWarpBytes + off) = lo;
           }
-          if (c32 & 1) {
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
-              const int c64 = n_idx * p.n_tile + (c32 >> 1) * 64;
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
 #pragma unroll
-              for (int pl = 0; pl < NPLANE; ++pl)
-                ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + c64, wq, hq, img + pl * p.n_img);
-              ptx::tma_store_commit();
-            }
+            for (int pl = 0; pl < NPLANE; ++pl)
+              ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + cb, wq, hq, img + pl * p.n_img);
+            ptx::tma_store_commit();
           }
         };
-        const int n32 = p.n_tile / 32;                   // even: NHWC outputs have Cout tiles that are multiples of 64
-        for (int c32 = 0; c32 < n32; c32 += 2) {
-          prefetch_res(c32 + 1, res_b);
+        for (int c32 = c_lo; c32 < c_hi; c32 += 2) {
+          if (c32 + 1 < c_hi) prefetch_res(c32 + 1, res_b);
           chunk(c32, res_a);
-          if (c32 + 2 < n32) prefetch_res(c32 + 2, res_a);
-          chunk(c32 + 1, res_b);
+          if (c32 + 1 < c_hi) {
+            if (c32 + 2 < c_hi) prefetch_res(c32 + 2, res_a);
+            chunk(c32 + 1, res_b);
+          }
         }
       } else {
-        for (int c16 = 0; c16 < p.n_tile / 16; ++c16) {
+        ptx::mbar_wait(&tmem_full_bar[as], aphase);
+        ptx::tc_fence_after();
+        const int n16 = p.n_tile / 16;
+        const int c_lo = half * ((n16 + 1) / 2), c_hi = half ? n16 : (n16 + 1) / 2;
+        float* out_px = p.out_nchw + ((long long)img * p.cout_real * p.out_h + h) * p.out_w + w;
+        const long long cstride = (long long)p.out_h * p.out_w;
+        for (int c16 = c_lo; c16 < c_hi; ++c16) {
           uint32_t r[16];
           float v[16];
           ptx::tmem_ld_32x32b_x16(taddr + c16 * 16, r);
           if (CORR) {
             uint32_t rc[16];
-            ptx::tmem_ld_32x32b_x16(taddr + 256 + c16 * 16, rc);
+            ptx::tmem_ld_32x32b_x16(taddr + p.corr_off + c16 * 16, rc);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
@@ -357,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             if (valid && c < p.cout_real) {
               float val = fmaf(v[j], p.wscale_inv, __ldg(p.bias + c));
               if (p.relu) val = fmaxf(val, 0.0f);
-              p.out_nchw[(((long long)img * p.cout_real + c) * p.out_h + h) * p.out_w + w] = val;
+              out_px[c * cstride] = val;
             }
           }
         }
@@ -535,7 +547,7 @@ struct BufferInfo {
 struct OpInfo {
   cnl_conv_desc d;
   // conv
-  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster;
+  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off;
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
@@ -572,11 +584,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const cuuint32_t* estride, const char* what) {
+                      const cuuint32_t* box, const cuuint32_t* estride, const char* what,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(CNL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides_bytes, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CNL_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
   return CNL_OK;
@@ -636,13 +649,18 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   op.store_h = 32 / op.store_w;
   const int planes = e->planes;
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
-  const int staging = dst.fp32_nchw ? 0 : 4 * planes * kStageWarpBytes;
+  const int staging = dst.fp32_nchw ? 0 : kEpiWarps * planes * kStageWarpBytes;
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / stage_bytes);
   if (op.num_stages < 2) return fail(CNL_ERR_UNSUPPORTED, "conv tile does not fit shared memory");
   op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
   // The separate correction accumulator pays off where the reduction is long (its rounding bias grows with the number
-  // of accumulate steps); short reductions (K < 576: stem, 1x1 convs) keep the double-buffered single one.
+  // of accumulate steps); short reductions (K < 576: stem, 1x1 convs) keep the single one.
   op.corr = (d.ksize * d.ksize * (d.cin / 64)) >= 9;
+  // TMEM: 512 columns = two accumulator stages of 256.  A correction accumulator sits 128 columns after the main one
+  // when the Cout tile is at most 128 wide; wider tiles need the whole 512 columns for one (main, correction) pair.
+  const bool split_corr = (e->precision == CNL_PRECISION_SPLIT) && op.corr;
+  op.corr_off = (op.n_tile <= 128) ? 128 : 256;
+  op.acc_stages = (split_corr && op.n_tile > 128) ? 1 : 2;
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = d.ksize * d.ksize;
@@ -692,9 +710,10 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   op.store_h = 32 / op.store_w;
   const int planes = e->planes;
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
-  op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - 4 * planes * kStageWarpBytes) / stage_bytes);
+  op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - kEpiWarps * planes * kStageWarpBytes) / stage_bytes);
   op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
   op.corr = false;                         // K = 256
+  op.corr_off = 128; op.acc_stages = 2;
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
@@ -807,10 +826,10 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       cuuint64_t str[3] = {128, sw * 128, sh * sw * 128};
       cuuint32_t es[4] = {1, 1, 1, 1};
       cuuint32_t box_in[4] = {64, (cuuint32_t)op.tw, (cuuint32_t)op.th, 1};
-      cuuint32_t box_out[4] = {64, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
+      cuuint32_t box_out[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
       int r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str, box_in, es, "stem im2row");
       if (r) return r;
-      r = encode_map(&op.dst_map, base + op.stem_s_offset, 4, dims, str, box_out, es, "stem out");
+      r = encode_map(&op.dst_map, base + op.stem_s_offset, 4, dims, str, box_out, es, "stem out", CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
       cuuint64_t wd[3] = {64, 64, (cuuint64_t)4 * planes};
       cuuint64_t ws[2] = {128, 64 * 128};
@@ -844,9 +863,9 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
     if (!dst.fp32_nchw) {
       cuuint64_t dims[4] = {(cuuint64_t)dst.channels, (cuuint64_t)dst.w, (cuuint64_t)dst.h, (cuuint64_t)e->batch * planes};
       cuuint64_t str[3] = {(cuuint64_t)dst.channels * 2, (cuuint64_t)dst.w * dst.channels * 2, (cuuint64_t)dst.h * dst.w * dst.channels * 2};
-      cuuint32_t box[4] = {64, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
+      cuuint32_t box[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};      // 32 channels = 64-byte rows
       cuuint32_t es[4] = {1, 1, 1, 1};
-      int r = encode_map(&op.dst_map, base + dst.offset, 4, dims, str, box, es, "dst");
+      int r = encode_map(&op.dst_map, base + dst.offset, 4, dims, str, box, es, "dst", CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
     } else {
       op.dst_map = op.src_map;
@@ -897,6 +916,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
+    p.acc_stages = op.acc_stages; p.corr_off = op.corr_off;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
