@@ -64,6 +64,7 @@ struct ConvParams {
   int corr_off;                 // column offset of the correction accumulator inside an accumulator stage (CORR only)
   int store_w, store_h;         // per-warp TMA store box in pixels (store_w * store_h == 32)
   int cluster;                  // CTAs per cluster sharing one multicast weight tile (1 = no cluster)
+  int cat;                      // CORR with Cout tile <= 128: hi*[hi|lo] issued as ONE MMA of N = 2*n_tile (see the MMA warp)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -174,6 +175,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     // ===================================== MMA issuer =================================================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
+      // cat: the hi and lo weight tiles sit back to back in the stage (n_tile rows of 128 B each, whole swizzle atoms),
+      // so A_hi x [B_hi | B_lo] is ONE instruction of N = 2*n_tile whose columns [n_tile, 2*n_tile) are the correction
+      // accumulator; only A_lo x B_hi is left as a second instruction.  The A tile is streamed from shared memory twice
+      // instead of three times per K step - narrow tiles (N = 64) are bound by exactly that operand bandwidth.
+      const uint32_t idesc_cat = ptx::make_idesc_f16_m128((uint32_t)p.n_tile * 2u);
+      const bool cat = CORR && p.cat;
       int stage = 0;
       uint32_t phase = 0;
       int acc_it = 0;
@@ -194,6 +201,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t koff = (uint64_t)((k * 32) >> 4);        // +32 bytes along K inside the swizzled row
+            if (NPLANE == 2 && cat) {
+              const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + kATileBytes);
+              ptx::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, (it | k) != 0);
+              ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
+              continue;
+            }
             ptx::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, (it | k) != 0);
             if (NPLANE == 2) {
               const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + kATileBytes);
@@ -547,7 +560,7 @@ struct BufferInfo {
 struct OpInfo {
   cnl_conv_desc d;
   // conv
-  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off;
+  int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off, cat;
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
@@ -608,6 +621,12 @@ static int choose_cluster(int n_tile, int m_tiles) {
   return c;
 }
 
+// CNL_CAT=0 switches the concatenated hi*[hi|lo] MMA off (A/B timing)
+static bool cat_enabled() {
+  static const bool on = [] { const char* v = getenv("CNL_CAT"); return !(v && atoi(v) == 0); }();
+  return on;
+}
+
 static void split_half(float x, __half* hi, __half* lo) {
   *hi = __float2half_rn(x);
   *lo = __float2half_rn(x - __half2float(*hi));
@@ -659,7 +678,11 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   // TMEM: 512 columns = two accumulator stages of 256.  A correction accumulator sits 128 columns after the main one
   // when the Cout tile is at most 128 wide; wider tiles need the whole 512 columns for one (main, correction) pair.
   const bool split_corr = (e->precision == CNL_PRECISION_SPLIT) && op.corr;
-  op.corr_off = (op.n_tile <= 128) ? 128 : 256;
+  // Cout tiles of at most 128 ("cat"): hi x [hi|lo] is one MMA of N = 2*n_tile, so the correction accumulator starts
+  // right after the main one and every such op runs with the separate accumulator, whatever its K.
+  op.cat = (e->precision == CNL_PRECISION_SPLIT) && op.n_tile <= 128 && cat_enabled();
+  if (op.cat) op.corr = true;
+  op.corr_off = op.cat ? op.n_tile : ((op.n_tile <= 128) ? 128 : 256);
   op.acc_stages = (split_corr && op.n_tile > 128) ? 1 : 2;
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
@@ -712,8 +735,9 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - kEpiWarps * planes * kStageWarpBytes) / stage_bytes);
   op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
-  op.corr = false;                         // K = 256
-  op.corr_off = 128; op.acc_stages = 2;
+  op.cat = (e->precision == CNL_PRECISION_SPLIT) && cat_enabled();
+  op.corr = op.cat;                        // K = 256: the correction accumulator only comes with the cat MMA
+  op.corr_off = op.cat ? 64 : 128; op.acc_stages = 2;
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
@@ -916,7 +940,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
-    p.acc_stages = op.acc_stages; p.corr_off = op.corr_off;
+    p.acc_stages = op.acc_stages; p.corr_off = op.corr_off; p.cat = op.cat;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
