@@ -85,44 +85,56 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
-// Class loop of one warp: rows [r0-P, r0+R+P) x columns [x0-P, x0+4+P) of classes [c_begin, c_end).
+// Class loop of one warp: rows [r0-P, r0+R+P) x columns [x0-P, x0+4*VEC+P) of classes [c_begin, c_end).
+// A lane owns 4*VEC consecutive columns (VEC float4 loads per row), the warp a tile of 128*VEC columns.
 // EDGE=false is the interior fast path (every row and column of the strip is inside the map: no predicates).
-template <int P, bool LOGITS, int R, bool MT, bool EDGE>
+template <int P, bool LOGITS, int R, bool MT, bool EDGE, int VEC>
 __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base, size_t plane, int c_begin, int c_end,
-                                                 int H, int W, int r0, int x0, int lane, bool col_ok,
-                                                 float (&best)[R][4]) {
+                                                 int H, int W, int r0, int x0, int lane,
+                                                 float (&best)[R][4 * VEC]) {
   constexpr int ROWS = R + 2 * P;
   constexpr int PH = (P > 0) ? P : 1;
+  constexpr int NC = 4 * VEC;                        // columns per lane
   const float NEG = -INFINITY;
   bool row_ok[ROWS];
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) { int r = r0 - P + j; row_ok[j] = !EDGE || (r >= 0 && r < H); }
+  bool col_ok[VEC];
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) col_ok[u] = !EDGE || (x0 + 4 * u < W);
   const float edge_l = (lane == 0) ? NEG : 0.0f, edge_r = (lane == 31) ? NEG : 0.0f;
 
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const float* pl = base + (size_t)c * plane;
-    float4 v[ROWS];
+    float4 v[ROWS][VEC];
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-      if (EDGE) v[j] = (row_ok[j] && col_ok) ? ld_stream4(pl + (long long)j * W) : make_float4(NEG, NEG, NEG, NEG);
-      else      v[j] = ld_stream4(pl + (long long)j * W);
-    }
+    for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        if (EDGE) v[j][u] = (row_ok[j] && col_ok[u]) ? ld_stream4(pl + (long long)j * W + 4 * u) : make_float4(NEG, NEG, NEG, NEG);
+        else      v[j][u] = ld_stream4(pl + (long long)j * W + 4 * u);
+      }
     if (LOGITS) {
       // saturation clamp (see kSatLogit) only when some logit of this warp's rows reaches it - rare in practice
-      float4 t4 = v[0];
+      float4 t4 = v[0][0];
 #pragma unroll
-      for (int j = 1; j < ROWS; ++j) t4 = max4(t4, v[j]);
+      for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) t4 = max4(t4, v[j][u]);
       const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
       if (__any_sync(0xffffffffu, tmax >= kSatLogit)) {
 #pragma unroll
         for (int j = 0; j < ROWS; ++j)
-          v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
+#pragma unroll
+          for (int u = 0; u < VEC; ++u)
+            v[j][u] = make_float4(fminf(v[j][u].x, kSatLogit), fminf(v[j][u].y, kSatLogit), fminf(v[j][u].z, kSatLogit),
+                                  fminf(v[j][u].w, kSatLogit));
       }
     }
-    // Halo columns of neighbouring column tiles (rows wider than one 128-column warp tile).  The neighbour shuffles
-    // below are rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the
-    // right" shuffle are free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
+    // Halo columns of neighbouring column tiles (rows wider than one warp tile).  The neighbour shuffles below are
+    // rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the right" shuffle
+    // are free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
     float hx[ROWS][PH];
     if constexpr (P > 0 && MT) {
 #pragma unroll
@@ -130,7 +142,7 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
 #pragma unroll
         for (int q = 0; q < P; ++q) {
           hx[j][q] = NEG;
-          const int xt = (lane == 31) ? (x0 - 124 - 1 - q) : (x0 + 128 + q);     // tile's first column - 1 - q / last + 1 + q
+          const int xt = (lane == 31) ? (x0 - 31 * NC - 1 - q) : (x0 + 32 * NC + q);     // tile's first column - 1 - q / last + 1 + q
           if ((lane == 0 || lane == 31) && row_ok[j] && xt >= 0 && xt < W) {
             float t = __ldg(pl + (long long)j * W + (xt - x0));
             hx[j][q] = LOGITS ? fminf(t, kSatLogit) : t;
@@ -140,7 +152,9 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       // vertical max over the window rows
-      float4 vm = v[i];
+      float4 vm[VEC];
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) vm[u] = v[i][u];
       float vh[PH];
       if constexpr (P > 0 && MT) {
 #pragma unroll
@@ -148,36 +162,42 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
       }
 #pragma unroll
       for (int j = 1; j <= 2 * P; ++j) {
-        vm = max4(vm, v[i + j]);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) vm[u] = max4(vm[u], v[i + j][u]);
         if constexpr (P > 0 && MT) {
 #pragma unroll
           for (int q = 0; q < P; ++q) vh[q] = fmaxf(vh[q], hx[i + j][q]);
         }
       }
-      // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+3] own, e[P+4..] right neighbours
-      float e[4 + 2 * P];
-      e[P + 0] = vm.x; e[P + 1] = vm.y; e[P + 2] = vm.z; e[P + 3] = vm.w;
+      // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+NC-1] own, e[P+NC..] right neighbours
+      float e[NC + 2 * P];
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        e[P + 4 * u + 0] = vm[u].x; e[P + 4 * u + 1] = vm[u].y; e[P + 4 * u + 2] = vm[u].z; e[P + 4 * u + 3] = vm[u].w;
+      }
       if constexpr (P > 0) {
-        const float own[4] = {vm.x, vm.y, vm.z, vm.w};
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-          // q-th column to the left of x0 is component (3-q) of lane-1; to the right of x0+3 it is component q of lane+1
-          float src_l = own[3 - q], src_r = own[q];
+          // q-th column to the left of x0 is the (NC-1-q)-th column of lane-1; to the right of x0+NC-1 it is column q of lane+1
+          float src_l = e[P + NC - 1 - q], src_r = e[P + q];
           if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
           float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
           float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
           if constexpr (!MT) { fl += edge_l; fr += edge_r; }      // -inf beyond the row ends (FADD: keeps the ALU pipe free)
           e[P - 1 - q] = fl;
-          e[P + 4 + q] = fr;
+          e[P + NC + q] = fr;
         }
       }
-      const float ctr[4] = {v[i + P].x, v[i + P].y, v[i + P].z, v[i + P].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float m = e[j];
+      for (int u = 0; u < VEC; ++u) {
+        const float ctr[4] = {v[i + P][u].x, v[i + P][u].y, v[i + P][u].z, v[i + P][u].w};
 #pragma unroll
-        for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[j + q]);
-        masked_max<LOGITS>(best[i][j], ctr[j], m);
+        for (int j = 0; j < 4; ++j) {
+          float m = e[4 * u + j];
+#pragma unroll
+          for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[4 * u + j + q]);
+          masked_max<LOGITS>(best[i][4 * u + j], ctr[j], m);
+        }
       }
     }
   }
@@ -197,61 +217,73 @@ __device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int P, bool LOGITS, int R, int G, bool MT>
-__global__ void __launch_bounds__(G * 32, (G == 4) ? 8 : 8)
+template <int P, bool LOGITS, int R, int G, bool MT, int VEC>
+__global__ void __launch_bounds__(G * 32, (R * VEC <= 4) ? 8 : 4)
 peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uint8_t* __restrict__ cgroup,
                   unsigned int* __restrict__ hist, int C, int H, int W) {
+  constexpr int NC = 4 * VEC;
+  constexpr int TW = kTW * VEC;                  // columns per warp tile
   const int lane = threadIdx.x & 31;
   const int g = threadIdx.x >> 5;
   const int n = blockIdx.z;
   const int r0 = blockIdx.y * R;
-  const int x0 = blockIdx.x * kTW + lane * 4;
-  const bool col_ok = x0 < W;
+  const int x0 = blockIdx.x * TW + lane * NC;
   const size_t plane = (size_t)H * W;
   const int cg = (C + G - 1) / G;
   const int c_begin = g * cg;
   const int c_end = min(C, c_begin + cg);
 
-  float best[R][4];
+  float best[R][NC];
 #pragma unroll
   for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) best[i][j] = best_init<LOGITS>();
+    for (int j = 0; j < NC; ++j) best[i][j] = best_init<LOGITS>();
 
   const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
-  const bool interior = (r0 - P >= 0) && (r0 + R + P <= H) && ((int)(blockIdx.x + 1) * kTW <= W);   // block-uniform
-  if (interior) peaks_class_loop<P, LOGITS, R, MT, false>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best);
-  else          peaks_class_loop<P, LOGITS, R, MT, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, col_ok, best);
+  const bool interior = (r0 - P >= 0) && (r0 + R + P <= H) && ((int)(blockIdx.x + 1) * TW <= W);   // block-uniform
+  if (interior) peaks_class_loop<P, LOGITS, R, MT, false, VEC>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
+  else          peaks_class_loop<P, LOGITS, R, MT, true, VEC>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
 
+  // every CTA is past its streaming loop: the select kernel's CTAs may be scheduled while this grid drains (they wait
+  // in griddepcontrol.wait until this grid has completed and flushed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // merge the G class groups through shared memory (a plain max), then emit one candidate per pixel
-  __shared__ __align__(16) float s_v[G][R][kTW];
+  __shared__ __align__(16) float s_v[G][R][TW];
   if (G > 1) {
 #pragma unroll
     for (int i = 0; i < R; ++i)
-      *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
+#pragma unroll
+      for (int u = 0; u < VEC; ++u)
+        *reinterpret_cast<float4*>(&s_v[g][i][lane * NC + 4 * u]) =
+            make_float4(best[i][4 * u], best[i][4 * u + 1], best[i][4 * u + 2], best[i][4 * u + 3]);
     __syncthreads();
   }
   for (int i = g; i < R; i += G) {          // warp g finishes rows g, g+G, ...
     int r = r0 + i;
-    if (r >= H || !col_ok) continue;
-    float bv[4];
-    uint32_t grp = 0;                        // which class group attained the maximum (first group on ties), 8 bits per pixel
+    if (r >= H) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (G > 1) {
-        bv[j] = s_v[0][i][lane * 4 + j];
+    for (int u = 0; u < VEC; ++u) {
+      const int xu = x0 + 4 * u;
+      if (xu >= W) continue;
+      float bv[4];
+      uint32_t grp = 0;                      // which class group attained the maximum (first group on ties), 8 bits per pixel
 #pragma unroll
-        for (int gg = 1; gg < G; ++gg) {
-          const float ov = s_v[gg][i][lane * 4 + j];
-          if (ov > bv[j]) { bv[j] = ov; grp = (grp & ~(0xffu << (8 * j))) | ((uint32_t)gg << (8 * j)); }
+      for (int j = 0; j < 4; ++j) {
+        if (G > 1) {
+          bv[j] = s_v[0][i][lane * NC + 4 * u + j];
+#pragma unroll
+          for (int gg = 1; gg < G; ++gg) {
+            const float ov = s_v[gg][i][lane * NC + 4 * u + j];
+            if (ov > bv[j]) { bv[j] = ov; grp = (grp & ~(0xffu << (8 * j))) | ((uint32_t)gg << (8 * j)); }
+          }
+        } else {
+          bv[j] = best[i][4 * u + j];
         }
-      } else {
-        bv[j] = best[i][j];
+        atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(bv[j]) >> kHistShift), 1u);
       }
-      atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(bv[j]) >> kHistShift), 1u);
+      *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + xu) = grp;
+      *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + xu) = make_float4(bv[0], bv[1], bv[2], bv[3]);
     }
-    *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + x0) = grp;
-    *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + x0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
   }
 }
 
@@ -358,7 +390,7 @@ peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __re
     const int cg = (C + G - 1) / G;
     const int c_begin = g * cg, c_end = min(C, c_begin + cg);
     const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
-    peaks_class_loop<P, LOGITS, R, false, true>(base, plane, c_begin, c_end, H, W, r0, x0, lane, true, best);
+    peaks_class_loop<P, LOGITS, R, false, true, 1>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
   }
 
   // merge the 4 warps' maxima through shared memory (aliases the ring)
@@ -608,6 +640,28 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, uint
   }
 }
 
+// Out-of-place descending rank sort of n <= kSelThreads DISTINCT 64-bit keys (the flat index is part of the key):
+// rank(i) = #{j : keys[j] > keys[i]}.  1024/pow2(n) threads (at most 32) share one element; one barrier instead of the
+// ~log2(n)^2/2 barriers of the bitonic network, which dominated the select kernel for the usual n of 100..256.
+__device__ __forceinline__ void rank_sort_desc(const unsigned long long* keys, const uint32_t* pay, int n,
+                                               unsigned long long* out_keys, uint32_t* out_pay, int tid) {
+  int np = 1;
+  while (np < n) np <<= 1;
+  int tpe = kSelThreads / np;                     // threads per element (power of two)
+  if (tpe > 32) tpe = 32;
+  const int i = tid / tpe, part = tid & (tpe - 1);
+  const bool act = i < n;
+  const unsigned long long mine = act ? keys[i] : 0ull;
+  int cnt = 0;
+  for (int j = part; j < n; j += tpe) cnt += (keys[j] > mine) ? 1 : 0;
+  for (int o = tpe >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (act && part == 0) {
+    out_keys[cnt] = mine;
+    if (pay != nullptr) out_pay[cnt] = pay[i];
+  }
+  __syncthreads();
+}
+
 // CACHE: H*W <= 16384 and a multiple of 4 - every thread keeps its 16 candidates in registers (loaded once, before
 // the histogram scan, so the L2 latency hides behind it); otherwise the passes re-read the candidate map from L2.
 template <bool CACHE>
@@ -622,6 +676,9 @@ select_gather_kernel(DecodeParams p) {
   const int n = blockIdx.x;
   const int tid = threadIdx.x;
   const int HW = p.H * p.W;
+  // launched with programmatic stream serialization: this grid may start while the peaks kernel drains; nothing the
+  // peaks kernel wrote may be read before it has completed and flushed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const float* sc = p.cscore + (size_t)n * HW;
   const int k = p.k;
   const bool vec4 = (HW & 3) == 0;
@@ -648,13 +705,22 @@ select_gather_kernel(DecodeParams p) {
         for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec);
       }
     } else {
-      for (int i0 = 0; i0 < n_vec; i0 += kSelThreads) {
-        const int i = i0 + tid;
-        const bool ok = i < n_vec;
-        const float4 v4 = ok ? sc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float fv[4] = {v4.x, v4.y, v4.z, v4.w};
+      // larger maps: 4 independent 16-byte loads per thread and round trip (the candidate map is L2-resident; one load
+      // per trip made every pass cost H*W/4096 L2 latencies)
+      for (int i0 = 0; i0 < n_vec; i0 += 4 * kSelThreads) {
+        float4 v4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, ok);
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * kSelThreads + tid;
+          v4[q] = (i < n_vec) ? sc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * kSelThreads + tid;
+          const float fv[4] = {v4[q].x, v4[q].y, v4[q].z, v4[q].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec);
+        }
       }
       for (int i0 = 4 * n_vec; i0 < HW; i0 += kSelThreads) {
         const int i = i0 + tid;
@@ -736,14 +802,19 @@ select_gather_kernel(DecodeParams p) {
     radix_select_fallback(sc, HW, k, s_list, s_hist, s_warp, s_scalars);
     n_sort = k;
   }
-  int kp = 1;
-  while (kp < n_sort) kp <<= 1;
+  // ---- sort, descending -------------------------------------------------------------------------------------
+  const unsigned long long* s_sorted = s_list;
   __syncthreads();
-  for (int i = n_sort + tid; i < kp; i += kSelThreads) s_list[i] = 0ull;
-  __syncthreads();
-
-  // ---- bitonic sort, descending ---------------------------------------------------------------------------
-  bitonic_sort_desc(s_list, nullptr, kp, tid);
+  if (n_sort <= kSelThreads) {                       // the usual case: k .. a few hundred collected candidates
+    rank_sort_desc(s_list, nullptr, n_sort, s_list + kSelThreads, nullptr, tid);
+    s_sorted = s_list + kSelThreads;
+  } else {
+    int kp = 1;
+    while (kp < n_sort) kp <<= 1;
+    for (int i = n_sort + tid; i < kp; i += kSelThreads) s_list[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s_list, nullptr, kp, tid);
+  }
 
   // ---- label recovery + score for the k winners ---------------------------------------------------------------
   // Reference: labels = argmax over classes of the MASKED map (first maximal class).  For a winner with best value v
@@ -762,7 +833,7 @@ select_gather_kernel(DecodeParams p) {
     int idx = 0;
     float v = 0.f;
     if (act) {
-      const unsigned long long w = s_list[j];
+      const unsigned long long w = s_sorted[j];
       idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
       v = key_to_float((uint32_t)(w >> 32));
     }
@@ -825,22 +896,23 @@ select_gather_kernel(DecodeParams p) {
     }
   }
   __syncthreads();
-  if (p.from_logits) {
-    int kq = 1;
-    while (kq < k) kq <<= 1;
-    for (int i = k + tid; i < kq; i += kSelThreads) { s_out[i] = 0ull; }
-    __syncthreads();
-    bitonic_sort_desc(s_out, s_label, kq, tid);
+  const unsigned long long* s_fin = s_out;
+  const uint32_t* s_fin_label = s_label;
+  if (p.from_logits) {                               // s_list is free again: sorted keys in its first half, labels behind
+    uint32_t* lab2 = reinterpret_cast<uint32_t*>(s_list + kSelThreads);
+    rank_sort_desc(s_out, s_label, k, s_list, lab2, tid);
+    s_fin = s_list;
+    s_fin_label = lab2;
   }
 
   // ---- gather + decode -------------------------------------------------------------------------------------
   for (int j = tid; j < k; j += kSelThreads) {
-    unsigned long long w = s_out[j];
+    unsigned long long w = s_fin[j];
     int idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
     size_t o = (size_t)n * k + j;
     p.scores[o] = key_to_float((uint32_t)(w >> 32));
     p.indices[o] = idx;
-    p.labels[o] = (long long)s_label[j];
+    p.labels[o] = (long long)s_fin_label[j];
     if (p.box == nullptr) continue;
     float4 b4 = decode_box(p.box + (size_t)n * 4 * plane, plane, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
     *reinterpret_cast<float4*>(p.boxes + o * 4) = b4;
@@ -849,7 +921,7 @@ select_gather_kernel(DecodeParams p) {
     const int E = p.E;
     for (int t = tid; t < k * E; t += kSelThreads) {
       int j = t / E, e = t - j * E;
-      int idx = (int)(0xffffffffu - (uint32_t)(s_out[j] & 0xffffffffull));
+      int idx = (int)(0xffffffffu - (uint32_t)(s_fin[j] & 0xffffffffull));
       p.emb[((size_t)n * k + j) * E + e] = __ldg(p.reid + ((size_t)n * E + e) * plane + idx);
     }
   }
@@ -858,16 +930,18 @@ select_gather_kernel(DecodeParams p) {
 // ------------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------------
-template <int P, bool LOGITS>
-static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
-                       cudaStream_t st) {
-  constexpr int R = 4;
-  dim3 grid((W + kTW - 1) / kTW, (H + R - 1) / R, N);
-  const bool mt = grid.x > 1;        // rows wider than one 128-column warp tile need halo columns from neighbours
+// Strip geometry.  R = rows per strip (the 2P halo rows are re-read by the neighbouring strips through L2: 50 % extra
+// L2 traffic at R = 4, 25 % at R = 8), VEC = float4 loads per lane and row (warp tile = 128*VEC columns; rows of up to
+// 256 columns then need no halo columns from a neighbouring tile).  CNL_PEAKS_R / CNL_PEAKS_VEC override the choice.
+template <int P, bool LOGITS, int R, int VEC>
+static int launch_fast_rv(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+                          cudaStream_t st) {
+  dim3 grid((W + kTW * VEC - 1) / (kTW * VEC), (H + R - 1) / R, N);
+  const bool mt = grid.x > 1;        // rows wider than one warp tile need halo columns from neighbours
 #define CNL_LAUNCH_PEAKS(G_)                                                                                      \
   do {                                                                                                            \
-    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W);  \
-    else    peaks_fast_kernel<P, LOGITS, R, G_, false><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W); \
+    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true, VEC><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W);  \
+    else    peaks_fast_kernel<P, LOGITS, R, G_, false, VEC><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W); \
   } while (0)
   int groups = 1;
   if (C >= 32) { CNL_LAUNCH_PEAKS(4); groups = 4; }
@@ -875,6 +949,22 @@ static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsign
   else CNL_LAUNCH_PEAKS(1);
 #undef CNL_LAUNCH_PEAKS
   return (C + groups - 1) / groups;          // classes per group, for the label recovery
+}
+
+template <int P, bool LOGITS>
+static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+                       cudaStream_t st) {
+  static const int env_r = getenv("CNL_PEAKS_R") ? atoi(getenv("CNL_PEAKS_R")) : 0;
+  static const int env_v = getenv("CNL_PEAKS_VEC") ? atoi(getenv("CNL_PEAKS_VEC")) : 0;
+  int vec = (W > kTW && W <= 2 * kTW) ? 2 : 1;
+  if (env_v == 1 || env_v == 2) vec = env_v;
+  int rows = 4;
+  if (env_r == 4 || env_r == 8) rows = env_r;
+  if constexpr (P == 1) {
+    if (vec == 2) return launch_fast_rv<P, LOGITS, 4, 2>(heat, cscore, cgroup, hist, N, C, H, W, st);
+    if (rows == 8) return launch_fast_rv<P, LOGITS, 8, 1>(heat, cscore, cgroup, hist, N, C, H, W, st);
+  }
+  return launch_fast_rv<P, LOGITS, 4, 1>(heat, cscore, cgroup, hist, N, C, H, W, st);
 }
 
 typedef CUresult (*EncodeTiledFnD)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -997,8 +1087,20 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   p.normalize = normalize_boxes; p.box_log = box_log; p.mult = box_multiplier; p.stride_f = (float)stride;
   p.boxes = boxes; p.scores = scores; p.labels = reinterpret_cast<long long*>(labels);
   p.indices = reinterpret_cast<long long*>(indices); p.emb = embeddings;
-  if ((h * w) % 4 == 0 && h * w <= 4 * 4 * kSelThreads) select_gather_kernel<true><<<n, kSelThreads, 0, st>>>(p);
-  else                                                  select_gather_kernel<false><<<n, kSelThreads, 0, st>>>(p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n);
+    cfg.blockDim = dim3(kSelThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // overlap this launch with the peaks kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if ((h * w) % 4 == 0 && h * w <= 4 * 4 * kSelThreads) CNL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, select_gather_kernel<true>, p));
+    else                                                  CNL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, select_gather_kernel<false>, p));
+  }
   CNL_CUDA_CHECK(cudaGetLastError());
   return CNL_OK;
 }
