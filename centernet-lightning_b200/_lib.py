@@ -23,6 +23,8 @@ class ConvDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
                 ("ksize", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("relu", C.c_int),
                 ("src_c_off", C.c_int), ("dst_c_off", C.c_int), ("residual", C.c_int), ("residual_up", C.c_int),
+                ("kh", C.c_int), ("kw", C.c_int), ("pad_h", C.c_int), ("pad_w", C.c_int),
+                ("dst_up", C.c_int), ("dst_phase", C.c_int),
                 ("weight_host", C.c_void_p), ("bias_host", C.c_void_p)]
 
 

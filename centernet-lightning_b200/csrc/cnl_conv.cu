@@ -65,6 +65,10 @@ struct ConvParams {
   int store_w, store_h;         // per-warp TMA store box in pixels (store_w * store_h == 32)
   int cluster;                  // CTAs per cluster sharing one multicast weight tile (1 = no cluster)
   int cat;                      // CORR with Cout tile <= 128: hi*[hi|lo] issued as ONE MMA of N = 2*n_tile (see the MMA warp)
+  int dst_up;                   // 2: the destination has twice the conv's output resolution (5-D store map, see below)
+  int dst_phase;                // dst_up == 2: -1 = write every pixel to its whole 2x2 block (conv + nearest x2 upsample),
+                                //              0..3 = write only sub-pixel (py, px) = (phase >> 1, phase & 1)
+  int dst_c;                    // channels of the destination buffer (dst_up == 2: sub-pixel px is folded into dim 0)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -339,9 +343,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           __syncwarp();
           if (lane == 0) {
             const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
+            if (p.dst_up == 2) {
+              // destination at twice the resolution, viewed as [n][y][py][x][px*C + c]: one store per sub-pixel.
+              // All four = conv followed by a nearest x2 upsample; a single one = one phase of a stride-2 transposed conv.
+              for (int ph = 0; ph < 4; ++ph) {
+                if (p.dst_phase >= 0 && ph != p.dst_phase) continue;
 #pragma unroll
-            for (int pl = 0; pl < NPLANE; ++pl)
-              ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + cb, wq, hq, img + pl * p.n_img);
+                for (int pl = 0; pl < NPLANE; ++pl)
+                  ptx::tma_store_5d(&dst_map, my_stage + pl * kStageWarpBytes, (ph & 1) * p.dst_c + p.dst_c_off + cb, wq, ph >> 1,
+                                    hq, img + pl * p.n_img);
+              }
+            } else {
+#pragma unroll
+              for (int pl = 0; pl < NPLANE; ++pl)
+                ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + cb, wq, hq, img + pl * p.n_img);
+            }
             ptx::tma_store_commit();
           }
         };
@@ -561,6 +577,7 @@ struct OpInfo {
   cnl_conv_desc d;
   // conv
   int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off, cat;
+  int kh, kw, pad_h, pad_w, up;         // resolved kernel extent / padding, destination scale (1 or 2)
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
@@ -641,9 +658,18 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   if (src.fp32_nchw) return fail(CNL_ERR_UNSUPPORTED, "conv input must be an NHWC fp16 buffer");
   if (d.cin % 64 || d.src_c_off % 64) return fail(CNL_ERR_UNSUPPORTED, "conv Cin/src_c_off must be multiples of 64 (got %d/%d)", d.cin, d.src_c_off);
   if (d.src_c_off + d.cin > src.channels) return fail(CNL_ERR_INVALID_ARGUMENT, "conv reads past the source channels");
-  if (d.ksize != 1 && d.ksize != 3) return fail(CNL_ERR_UNSUPPORTED, "conv kernel size %d (1 and 3 are implemented)", d.ksize);
+  // kernel extent: ksize x ksize with symmetric padding, or an explicit kh x kw window with its own top/left padding
+  // (the sub-pixel phases of a stride-2 transposed conv are 1x1 / 1x2 / 2x1 / 2x2 windows)
+  op.kh = d.kh > 0 ? d.kh : d.ksize; op.kw = d.kw > 0 ? d.kw : d.ksize;
+  op.pad_h = d.kh > 0 ? d.pad_h : d.pad; op.pad_w = d.kw > 0 ? d.pad_w : d.pad;
+  op.up = d.dst_up == 2 ? 2 : 1;
+  if (op.kh < 1 || op.kh > 3 || op.kw < 1 || op.kw > 3) return fail(CNL_ERR_UNSUPPORTED, "conv window %dx%d (1..3 per side are implemented)", op.kh, op.kw);
+  if (op.pad_h < 0 || op.pad_h >= 3 || op.pad_w < 0 || op.pad_w >= 3) return fail(CNL_ERR_INVALID_ARGUMENT, "conv padding %d/%d", op.pad_h, op.pad_w);
   if (d.stride != 1 && d.stride != 2) return fail(CNL_ERR_UNSUPPORTED, "conv stride %d", d.stride);
-  if (src.h / d.stride != dst.h || src.w / d.stride != dst.w) return fail(CNL_ERR_INVALID_ARGUMENT, "conv output size mismatch");
+  if (d.dst_up != 0 && d.dst_up != 1 && d.dst_up != 2) return fail(CNL_ERR_INVALID_ARGUMENT, "conv dst_up %d", d.dst_up);
+  if (op.up == 2 && (d.dst_phase < -1 || d.dst_phase > 3)) return fail(CNL_ERR_INVALID_ARGUMENT, "conv dst_phase %d", d.dst_phase);
+  if (op.up == 2 && (dst.fp32_nchw || d.residual >= 0)) return fail(CNL_ERR_UNSUPPORTED, "an upsampling store needs an NHWC destination and no residual");
+  if (src.h / d.stride * op.up != dst.h || src.w / d.stride * op.up != dst.w) return fail(CNL_ERR_INVALID_ARGUMENT, "conv output size mismatch");
   if (d.cout % 256 == 0) { op.n_tile = 256; op.cout_pad = d.cout; }
   else if (d.cout <= 256) { op.cout_pad = (d.cout + 15) / 16 * 16; op.n_tile = op.cout_pad; }
   else return fail(CNL_ERR_UNSUPPORTED, "conv Cout=%d (must be <= 256 or a multiple of 256)", d.cout);
@@ -660,10 +686,11 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
     if (rb.channels != d.cout || rb.h * d.residual_up != dst.h || rb.w * d.residual_up != dst.w)
       return fail(CNL_ERR_INVALID_ARGUMENT, "residual shape mismatch");
   }
-  op.tw = std::max(8, std::min(128, pow2_ceil(dst.w)));
+  const int out_w = dst.w / op.up, out_h = dst.h / op.up;      // the conv's own output grid
+  op.tw = std::max(8, std::min(128, pow2_ceil(out_w)));
   op.th = kBlockM / op.tw;
-  op.tiles_w = (dst.w + op.tw - 1) / op.tw;
-  op.tiles_h = (dst.h + op.th - 1) / op.th;
+  op.tiles_w = (out_w + op.tw - 1) / op.tw;
+  op.tiles_h = (out_h + op.th - 1) / op.th;
   op.store_w = std::min(op.tw, 32);
   op.store_h = 32 / op.store_w;
   const int planes = e->planes;
@@ -674,7 +701,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
   // The separate correction accumulator pays off where the reduction is long (its rounding bias grows with the number
   // of accumulate steps); short reductions (K < 576: stem, 1x1 convs) keep the single one.
-  op.corr = (d.ksize * d.ksize * (d.cin / 64)) >= 9;
+  op.corr = (op.kh * op.kw * (d.cin / 64)) >= 9;
   // TMEM: 512 columns = two accumulator stages of 256.  A correction accumulator sits 128 columns after the main one
   // when the Cout tile is at most 128 wide; wider tiles need the whole 512 columns for one (main, correction) pair.
   const bool split_corr = (e->precision == CNL_PRECISION_SPLIT) && op.corr;
@@ -686,7 +713,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   op.acc_stages = (split_corr && op.n_tile > 128) ? 1 : 2;
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
-  const int taps = d.ksize * d.ksize;
+  const int taps = op.kh * op.kw;
   std::vector<float> wt((size_t)d.cout * taps * d.cin);
   for (int co = 0; co < d.cout; ++co)
     for (int ci = 0; ci < d.cin; ++ci)
@@ -725,6 +752,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   // inner conv: 4 vertical taps over the im2row tensor, Cin = 64 (48 used), Cout = 64, at half resolution
   const int sw = e->width / 2, sh = e->height / 2;
   op.cout_pad = 64; op.n_tile = 64; op.n_tiles = 1;
+  op.kh = 4; op.kw = 1; op.pad_h = 2; op.pad_w = 0; op.up = 1;
   op.tw = std::max(8, std::min(128, pow2_ceil(sw)));
   op.th = kBlockM / op.tw;
   op.tiles_w = (sw + op.tw - 1) / op.tw;
@@ -867,7 +895,7 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
     CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.bias_offset, op.bias_packed.data(), op.bias_packed.size() * 4, cudaMemcpyHostToDevice, st));
     const BufferInfo& src = e->bufs[d.src];
     const BufferInfo& dst = e->bufs[d.dst];
-    const int taps = d.ksize * d.ksize;
+    const int taps = op.kh * op.kw;
     {
       cuuint64_t dims[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.w, (cuuint64_t)src.h, (cuuint64_t)e->batch * planes};
       cuuint64_t str[3] = {(cuuint64_t)src.channels * 2, (cuuint64_t)src.w * src.channels * 2, (cuuint64_t)src.h * src.w * src.channels * 2};
@@ -884,7 +912,16 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       int r = encode_map(&op.w_map, base + op.w_offset, 3, dims, str, box, es, "weights");
       if (r) return r;
     }
-    if (!dst.fp32_nchw) {
+    if (!dst.fp32_nchw && op.up == 2) {
+      // [n][y][py][x][px*C + c] view of the double-resolution NHWC destination (sub-pixel px folded into dim 0)
+      const cuuint64_t C2 = (cuuint64_t)dst.channels, ow = dst.w / 2, oh = dst.h / 2;
+      cuuint64_t dims[5] = {2 * C2, ow, 2, oh, (cuuint64_t)e->batch * planes};
+      cuuint64_t str[4] = {2 * C2 * 2, 2 * ow * C2 * 2, 4 * ow * C2 * 2, 4 * oh * ow * C2 * 2};
+      cuuint32_t box[5] = {32, (cuuint32_t)op.store_w, 1, (cuuint32_t)op.store_h, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      int r = encode_map(&op.dst_map, base + dst.offset, 5, dims, str, box, es, "dst (x2)", CU_TENSOR_MAP_SWIZZLE_64B);
+      if (r) return r;
+    } else if (!dst.fp32_nchw) {
       cuuint64_t dims[4] = {(cuuint64_t)dst.channels, (cuuint64_t)dst.w, (cuuint64_t)dst.h, (cuuint64_t)e->batch * planes};
       cuuint64_t str[3] = {(cuuint64_t)dst.channels * 2, (cuuint64_t)dst.w * dst.channels * 2, (cuuint64_t)dst.h * dst.w * dst.channels * 2};
       cuuint32_t box[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};      // 32 channels = 64-byte rows
@@ -941,6 +978,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
     p.acc_stages = op.acc_stages; p.corr_off = op.corr_off; p.cat = op.cat;
+    p.dst_up = 1; p.dst_phase = -1; p.dst_c = dst.channels;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
@@ -964,8 +1002,9 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
       CNL_CUDA_CHECK(cudaGetLastError());
       continue;
     }
-    p.out_h = dst.h; p.out_w = dst.w;
-    p.kh = d.ksize; p.kw = d.ksize; p.stride = d.stride; p.pad_h = d.pad; p.pad_w = d.pad; p.kblocks = d.cin / 64;
+    p.out_h = dst.h / op.up; p.out_w = dst.w / op.up;
+    p.dst_up = op.up; p.dst_phase = d.dst_phase;
+    p.kh = op.kh; p.kw = op.kw; p.stride = d.stride; p.pad_h = op.pad_h; p.pad_w = op.pad_w; p.kblocks = d.cin / 64;
     p.src_c_off = d.src_c_off; p.dst_c_off = d.dst_c_off;
     p.out_mode = dst.fp32_nchw ? 1 : 0;
     p.cout_real = d.cout;

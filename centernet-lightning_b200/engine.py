@@ -46,6 +46,7 @@ class Engine:
                 1 if op.kind == "stem" else 0, self.buffer_ids[op.src], self.buffer_ids[op.dst], op.cin, op.cout,
                 op.ksize, op.stride, op.pad, int(op.relu), op.src_c_off, op.dst_c_off,
                 self.buffer_ids[op.residual] if op.residual is not None else -1, op.residual_up,
+                op.kh, op.kw, op.pad_h, op.pad_w, op.dst_up, op.dst_phase,
                 w.ctypes.data, b.ctypes.data)
         handle = C.c_void_p()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()

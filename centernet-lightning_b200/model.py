@@ -94,6 +94,36 @@ class _FPN(nn.Module):
         return self.out_channels
 
 
+class _SimpleNeck(nn.Module):
+    """G1 "simple" neck (reference configs/base_resnet34.yaml:7-11, models/layers.py:71-99):
+    on C5 only, n x [conv3x3-BN-ReLU -> x2 upsample], upsample = nearest or ConvTranspose2d-BN-ReLU."""
+
+    def __init__(self, in_channels, upsample_channels=(256, 128, 64), upsample_type="nearest", deconv_kernel=3,
+                 conv_type="normal"):
+        super().__init__()
+        if upsample_type not in ("nearest", "conv_transpose"):
+            raise ValueError(f"upsample_type {upsample_type!r}: the sm_100a engine lowers 'nearest' and 'conv_transpose'")
+        if conv_type != "normal":
+            raise ValueError(f"conv_type {conv_type!r}: the sm_100a engine lowers 'normal' convolutions")
+        if deconv_kernel not in (3, 4):
+            raise ValueError("deconv_kernel must be 3 or 4")
+        if any(c % 64 for c in upsample_channels):
+            raise ValueError("upsample_channels must be multiples of 64")
+        self.stride = 2 ** len(upsample_channels)
+        chans = [in_channels[-1], *upsample_channels]
+        self.blocks = nn.ModuleList([_ConvBn(chans[i], chans[i + 1]) for i in range(len(upsample_channels))])
+        self.out_channels = chans[-1]
+        if upsample_type == "conv_transpose":
+            op = deconv_kernel % 2
+            self.up = nn.ModuleList([
+                nn.Sequential(nn.ConvTranspose2d(c, c, deconv_kernel, stride=2, padding=(deconv_kernel + op) // 2 - 1,
+                                                 output_padding=op, bias=False), nn.BatchNorm2d(c))
+                for c in upsample_channels])
+
+    def get_out_channels(self):
+        return self.out_channels
+
+
 class _Head(nn.Module):
     def __init__(self, cin, cout, width=256, depth=3, init_bias=None):
         super().__init__()
@@ -109,10 +139,12 @@ class EngineModel(nn.Module):
     """Stands where the reference's GenericModel stands (``CenterNet.model``): same parameters, same call contract
     ``model(images) -> Dict[str, Tensor]`` of raw head outputs, executed by the sm_100a engine."""
 
-    def __init__(self, backbone: _Backbone, neck: _FPN, heads: nn.Module, precision: int, backbone_name: str = "resnet34"):
+    def __init__(self, backbone: _Backbone, neck: nn.Module, heads: nn.Module, precision: int, backbone_name: str = "resnet34",
+                 neck_name: str = "FPN"):
         super().__init__()
         self.backbone, self.neck, self.heads = backbone, neck, heads
         self.backbone_name = backbone_name
+        self.neck_name = neck_name
         self.precision = precision
         self._engines: Dict[Tuple, Engine] = {}
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
@@ -133,7 +165,8 @@ class EngineModel(nn.Module):
         if eng is None:
             names = self.head_names()
             depth = getattr(self.heads, names[0]).depth
-            plan = build_plan(self.state_dict(), backbone=self.backbone_name, head_names=names, head_depth=depth)
+            plan = build_plan(self.state_dict(), backbone=self.backbone_name, neck=self.neck_name, head_names=names,
+                              head_depth=depth)
             eng = Engine(plan, n, h, w, images.device, precision=self.precision)
             self._engines[key] = eng
         return eng
@@ -161,8 +194,8 @@ class CenterNet(nn.Module):
         super().__init__()
         if pretrained_backbone:
             raise RuntimeError("pretrained_backbone=True needs a download; load weights with load_state_dict() instead")
-        if neck != "FPN":
-            raise ValueError(f"neck {neck!r}: the sm_100a engine lowers the FPN neck (SURVEY 8a F2)")
+        if neck not in ("FPN", "simple", "SimpleNeck"):
+            raise ValueError(f"neck {neck!r}: the sm_100a engine lowers the FPN and simple necks (SURVEY 8a F2, 8f rank 4)")
         if nms_kernel % 2 != 1:
             raise ValueError("nms_kernel must be odd")
         neck_config = dict(neck_config or {})
@@ -172,14 +205,14 @@ class CenterNet(nn.Module):
                                        heatmap_prior=heatmap_prior, nms_kernel=nms_kernel, num_detections=num_detections,
                                        reid_dim=reid_dim, precision=precision, **training_only)
         bb = _Backbone(backbone)
-        nk = _FPN(bb.get_out_channels(), **neck_config)
+        nk = _FPN(bb.get_out_channels(), **neck_config) if neck == "FPN" else _SimpleNeck(bb.get_out_channels(), **neck_config)
         heads = nn.Module()
         c = nk.get_out_channels()
         heads.add_module("heatmap", _Head(c, num_classes, init_bias=math.log(heatmap_prior / (1 - heatmap_prior)), **head_config))
         heads.add_module("box_2d", _Head(c, 4, init_bias=box_init_bias, **head_config))
         if reid_dim:
             heads.add_module("reid", _Head(c, reid_dim, **head_config))
-        self.model = EngineModel(bb, nk, heads, _PRECISIONS[precision], backbone)
+        self.model = EngineModel(bb, nk, heads, _PRECISIONS[precision], backbone, neck)
         self.stride = bb.stride // nk.stride                                   # reference models/meta.py:96
         self.num_classes = num_classes
         self._graphs: Dict[Tuple, Any] = {}

@@ -54,10 +54,21 @@ class ConvOp:
     dst_c_off: int = 0
     residual: Optional[str] = None      # buffer added before ReLU
     residual_up: int = 1                # 2 = residual is the half-resolution map, nearest-upsampled (FPN)
+    kh: int = 0                         # explicit (non-square) window with its own top/left padding; 0 = ksize x ksize
+    kw: int = 0
+    pad_h: int = 0
+    pad_w: int = 0
+    dst_up: int = 1                     # 2 = dst has twice the conv's output resolution
+    dst_phase: int = -1                 # dst_up == 2: -1 = fill each 2x2 block (nearest x2), 0..3 = one sub-pixel (py*2+px)
+
+    @property
+    def window(self) -> Tuple[int, int]:
+        return (self.kh or self.ksize, self.kw or self.ksize)
 
     @property
     def macs_per_out_pixel(self) -> int:
-        return self.cin * self.cout * self.ksize * self.ksize
+        kh, kw = self.window
+        return self.cin * self.cout * kh * kw
 
 
 @dataclass
@@ -78,6 +89,7 @@ class Plan:
             s = self.buffers[op.dst].stride
             if op.kind == "stem":
                 s = 2                                   # conv output is at stride 2, pooled to 4
+            s *= op.dst_up                              # upsampling stores: the conv runs at half the dst resolution
             total += (height // s) * (width // s) * op.macs_per_out_pixel
         return total
 
@@ -97,6 +109,36 @@ def fold_bn(weight: torch.Tensor, bn: Optional[Dict[str, torch.Tensor]], conv_bi
 
 def _bn(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
     return {k: sd[f"{prefix}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
+
+
+def lower_conv_transpose(name: str, src: str, dst: str, weight: torch.Tensor, bn: Optional[Dict[str, torch.Tensor]],
+                         relu: bool = True) -> List[ConvOp]:
+    """ConvTranspose2d(C_in, C_out, k, stride=2, padding=p, output_padding=k%2, bias=False) [+ BN + ReLU] as the
+    reference builds it (models/layers.py:86-96: k=3 -> p=1, output_padding=1; k=4 -> p=1) lowered to four ordinary
+    convolutions, one per output sub-pixel (py, px):
+
+        out[2y+py, 2x+px] = sum_{dy,dx} in[y+dy, x+dx] * W[:, :, py+p-2dy, px+p-2dx]     (taps inside the kernel only)
+
+    i.e. a (1..2)x(1..2) correlation window with top/left padding -dy_min/-dx_min whose result lands on sub-pixel
+    (py, px) of the double-resolution destination.  ``weight`` is torch's (C_in, C_out, k, k)."""
+    cin, cout, k, k2 = weight.shape
+    if k != k2 or k not in (3, 4):
+        raise ValueError(f"conv_transpose kernel {k}x{k2}: 3 and 4 are implemented (reference models/layers.py:86-96)")
+    pad = (k + k % 2) // 2 - 1
+    # fold BN (per output channel = dim 1 of the transposed-conv weight)
+    w_f, b_f = fold_bn(weight.permute(1, 0, 2, 3).contiguous(), bn)          # (cout, cin, k, k)
+    ops = []
+    for py in range(2):
+        dys = [dy for dy in (-1, 0, 1) if 0 <= py + pad - 2 * dy < k]
+        for px in range(2):
+            dxs = [dx for dx in (-1, 0, 1) if 0 <= px + pad - 2 * dx < k]
+            wp = torch.empty((cout, cin, len(dys), len(dxs)), dtype=torch.float32)
+            for r, dy in enumerate(dys):
+                for c, dx in enumerate(dxs):
+                    wp[:, :, r, c] = w_f[:, :, py + pad - 2 * dy, px + pad - 2 * dx]
+            ops.append(ConvOp(f"{name}.phase{py}{px}", "conv", src, dst, cin, cout, 0, 1, 0, wp.contiguous(), b_f, relu=relu,
+                              kh=len(dys), kw=len(dxs), pad_h=-dys[0], pad_w=-dxs[0], dst_up=2, dst_phase=py * 2 + px))
+    return ops
 
 
 def build_plan(sd: Dict[str, torch.Tensor], *, backbone: str = "resnet34", neck: str = "FPN",
@@ -151,8 +193,31 @@ def build_plan(sd: Dict[str, torch.Tensor], *, backbone: str = "resnet34", neck:
             x = p.add_buffer(f"neck.out{i}", d, s)
             p.ops.append(ConvOp(f"neck.output.{i}", "conv", fused, x, d, d, 3, 1, 1, w, b, relu=True))
         neck_out, neck_c, neck_stride = x, d, 4
+    elif neck in ("simple", "SimpleNeck"):
+        # G1 "simple" neck (reference configs/base_resnet34.yaml:7-11, models/layers.py:71-99): on C5 only,
+        # n x [conv3x3-BN-ReLU -> x2 upsample]; the upsample is nearest (fused into the conv's store: every output pixel
+        # is written to its 2x2 block) or ConvTranspose2d(k, stride 2)-BN-ReLU (four sub-pixel phase convs).
+        x, cin_n, s = feats[3], 512, 32
+        i = 0
+        while f"neck.blocks.{i}.conv.weight" in sd:
+            w, b = fold_bn(sd[f"neck.blocks.{i}.conv.weight"], _bn(sd, f"neck.blocks.{i}.bn"))
+            c = w.shape[0]
+            if f"neck.up.{i}.0.weight" in sd:
+                y = p.add_buffer(f"neck.conv{i}", c, s)
+                p.ops.append(ConvOp(f"neck.blocks.{i}", "conv", x, y, cin_n, c, 3, 1, 1, w, b, relu=True))
+                up = p.add_buffer(f"neck.up{i}", c, s // 2)
+                for op in lower_conv_transpose(f"neck.up.{i}", y, up, sd[f"neck.up.{i}.0.weight"], _bn(sd, f"neck.up.{i}.1")):
+                    p.ops.append(op)
+            else:
+                up = p.add_buffer(f"neck.up{i}", c, s // 2)
+                p.ops.append(ConvOp(f"neck.blocks.{i}", "conv", x, up, cin_n, c, 3, 1, 1, w, b, relu=True, dst_up=2, dst_phase=-1))
+            x, cin_n, s = up, c, s // 2
+            i += 1
+        if i == 0:
+            raise ValueError("simple neck: no neck.blocks.* parameters in the state dict")
+        neck_out, neck_c, neck_stride = x, cin_n, s
     else:
-        raise ValueError(f"neck {neck!r} is not lowered by the sm_100a engine (FPN only; SURVEY 8a F2)")
+        raise ValueError(f"neck {neck!r} is not lowered by the sm_100a engine (FPN and simple; SURVEY 8a F2, 8f rank 4)")
     p.model_stride = neck_stride
 
     # ---- heads: first tower layers fused across heads ------------------------------------------

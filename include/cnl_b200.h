@@ -116,7 +116,14 @@ typedef struct {
   int src_c_off, dst_c_off;
   int residual;        /* buffer id or -1                                                                 */
   int residual_up;     /* 1 or 2 (nearest-upsampled half-resolution residual)                             */
-  const float* weight_host;   /* (cout, cin, k, k) fp32, BatchNorm already folded                         */
+  int kh, kw;          /* explicit window (1..3 per side); 0 = ksize x ksize with symmetric `pad`         */
+  int pad_h, pad_w;    /* top / left zero padding of the explicit window                                  */
+  int dst_up;          /* 0/1 = dst has the conv's output size; 2 = dst has twice that size               */
+  int dst_phase;       /* dst_up == 2: -1 = each output pixel fills its 2x2 block (conv + nearest x2
+                          upsample, reference models/layers.py:98-99); 0..3 = only sub-pixel
+                          (py, px) = (phase >> 1, phase & 1) is written: one phase of a stride-2
+                          ConvTranspose2d (reference models/layers.py:86-96)                              */
+  const float* weight_host;   /* (cout, cin, kh, kw) fp32, BatchNorm already folded                       */
   const float* bias_host;     /* (cout,) fp32                                                             */
 } cnl_conv_desc;
 

@@ -138,24 +138,39 @@ class FPN(nn.Module):
 
 
 class SimpleNeck(nn.Module):
-    """BASELINE config 1 neck: 3 x [ConvBnAct3x3 -> nearest x2]
+    """BASELINE config 1 neck: 3 x [ConvBnAct3x3 -> x2 upsample]
     on C5 only, channels 512->256->128->64 (configs/base_resnet34.yaml:7-11,
-    tests/test_necks.py:23-38)."""
+    tests/test_necks.py:23-38).  ``upsample_type``: "nearest" (the shipped config) or
+    "conv_transpose" = ConvTranspose2d(c, c, k, stride=2, padding, output_padding,
+    bias=False) -> BN -> ReLU exactly as models/layers.py:86-96 builds it
+    (output_padding = k % 2, padding = (k + output_padding) // 2 - 1)."""
 
-    def __init__(self, in_channels: List[int], upsample_channels=(256, 128, 64)):
+    def __init__(self, in_channels: List[int], upsample_channels=(256, 128, 64), upsample_type: str = "nearest",
+                 deconv_kernel: int = 3):
         super().__init__()
+        assert upsample_type in ("nearest", "conv_transpose")
         self.stride = 2 ** len(upsample_channels)
         chans = [in_channels[-1], *upsample_channels]
         self.blocks = nn.ModuleList([ConvBnAct(chans[i], chans[i + 1]) for i in range(len(upsample_channels))])
         self.out_channels = chans[-1]
+        self.upsample_type = upsample_type
+        if upsample_type == "conv_transpose":
+            output_padding = deconv_kernel % 2
+            padding = (deconv_kernel + output_padding) // 2 - 1
+            self.up = nn.ModuleList([
+                nn.Sequential(nn.ConvTranspose2d(c, c, deconv_kernel, stride=2, padding=padding,
+                                                 output_padding=output_padding, bias=False),
+                              nn.BatchNorm2d(c), nn.ReLU(inplace=True))
+                for c in upsample_channels])
 
     def get_out_channels(self) -> int:
         return self.out_channels
 
     def forward(self, feats: List[torch.Tensor]) -> torch.Tensor:
         x = feats[-1]
-        for blk in self.blocks:
-            x = F.interpolate(blk(x), scale_factor=2.0, mode="nearest")
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            x = self.up[i](x) if self.upsample_type == "conv_transpose" else F.interpolate(x, scale_factor=2.0, mode="nearest")
         return x
 
 
@@ -235,6 +250,10 @@ def synth_init(model: SpecModel, seed: int = 0, calib_size: int = 128, calib_bat
             mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
             if mod.bias is not None and mod is not model.heads.heatmap.out_conv:
                 mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)    # heatmap keeps its prior bias
+        elif isinstance(mod, nn.ConvTranspose2d):
+            # every output pixel of a stride-2 transposed conv sees about k*k/4 taps per input channel
+            fan_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1] / 4.0
+            mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
         elif isinstance(mod, nn.BatchNorm2d):
             mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
             mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)

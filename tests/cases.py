@@ -65,6 +65,13 @@ def make_decode_inputs(case):
 FORWARD_CASES = {
     "det64": dict(model=dict(num_classes=80), seed=0, n=2, size=64, img_seed=7),
     "track64": dict(model=dict(num_classes=2, reid_dim=64), seed=1, n=1, size=64, img_seed=8),
+    # BASELINE configs[0] (configs/base_resnet34.yaml): ResNet-34 + "simple" neck (no FPN), nearest x2 upsampling
+    "simple64": dict(model=dict(num_classes=80, neck="simple"), seed=2, n=2, size=64, img_seed=9),
+    # the same neck with the reference's ConvTranspose2d-BN-ReLU upsample layers (models/layers.py:86-96), k = 3 and 4
+    "deconv3_64": dict(model=dict(num_classes=80, neck="simple", neck_config=dict(upsample_type="conv_transpose", deconv_kernel=3)),
+                       seed=3, n=1, size=64, img_seed=10),
+    "deconv4_64": dict(model=dict(num_classes=80, neck="simple", neck_config=dict(upsample_type="conv_transpose", deconv_kernel=4)),
+                       seed=4, n=1, size=64, img_seed=11),
 }
 
 

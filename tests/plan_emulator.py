@@ -25,14 +25,19 @@ def _q(x: torch.Tensor, dtype: Optional[torch.dtype], split: bool) -> torch.Tens
 
 @torch.no_grad()
 def run_plan(plan, image: torch.Tensor, act_dtype: Optional[torch.dtype] = None, split: bool = False,
-             conv_dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+             conv_dtype: torch.dtype = torch.float32, extra: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     bufs: Dict[str, torch.Tensor] = {"image": image}
+    bufs.update(extra or {})
     for op in plan.ops:
         x = bufs[op.src]
         if op.kind != "stem":
             x = x[:, op.src_c_off:op.src_c_off + op.cin]
         w = _q(op.weight, act_dtype, split)
-        y = F.conv2d(x.to(conv_dtype), w.to(conv_dtype), None, op.stride, op.pad).float()
+        if op.kh:                                   # explicit window with top/left padding (transposed-conv phases)
+            xp = F.pad(x, (op.pad_w, op.kw - 1 - op.pad_w, op.pad_h, op.kh - 1 - op.pad_h))
+            y = F.conv2d(xp.to(conv_dtype), w.to(conv_dtype), None, op.stride, 0).float()
+        else:
+            y = F.conv2d(x.to(conv_dtype), w.to(conv_dtype), None, op.stride, op.pad).float()
         y = y + op.bias.view(1, -1, 1, 1)
         if op.residual is not None:
             r = bufs[op.residual]
@@ -46,8 +51,15 @@ def run_plan(plan, image: torch.Tensor, act_dtype: Optional[torch.dtype] = None,
         dst = plan.buffers[op.dst]
         if not dst.fp32_nchw:
             y = _q(y, act_dtype, split)
+        up = op.dst_up
         if op.dst not in bufs:
             n, _, h, wd = y.shape
-            bufs[op.dst] = torch.zeros((n, dst.channels, h, wd))
-        bufs[op.dst][:, op.dst_c_off:op.dst_c_off + op.cout] = y
+            bufs[op.dst] = torch.zeros((n, dst.channels, h * up, wd * up))
+        if up == 2 and op.dst_phase < 0:            # conv + nearest x2
+            bufs[op.dst][:, op.dst_c_off:op.dst_c_off + op.cout] = F.interpolate(y, scale_factor=2.0, mode="nearest")
+        elif up == 2:                               # one sub-pixel phase
+            py, px = op.dst_phase >> 1, op.dst_phase & 1
+            bufs[op.dst][:, op.dst_c_off:op.dst_c_off + op.cout, py::2, px::2] = y
+        else:
+            bufs[op.dst][:, op.dst_c_off:op.dst_c_off + op.cout] = y
     return {h: bufs[b] for h, b in plan.outputs.items()}

@@ -57,3 +57,41 @@ def test_split_precision_meets_parity_bar_and_single_pass_does_not(det):
     for k in ref:
         assert (split[k] - ref[k]).abs().max() < 1e-3
     assert max((single[k] - ref[k]).abs().max() for k in ref) > 1e-3
+
+
+@pytest.mark.parametrize("case", ["simple64", "deconv3_64", "deconv4_64"])
+def test_simple_neck_plan_reproduces_oracle(case):
+    """BASELINE configs[0] neck: conv + nearest x2 as an upsampling store; ConvTranspose2d(k=3/4, stride 2) as four
+    sub-pixel phase convolutions (reference models/layers.py:86-99)."""
+    kw = cases.FORWARD_CASES[case]
+    m = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"])
+    pl = P.build_plan(m.state_dict(), neck="simple")
+    x = cases.make_image(kw)
+    with torch.no_grad():
+        ref = m(x)
+    out = run_plan(pl, x)
+    for k in ref:
+        assert out[k].shape == ref[k].shape
+        np.testing.assert_allclose(out[k].numpy(), ref[k].numpy(), rtol=0, atol=2e-4)
+    n_phase = sum(1 for op in pl.ops if op.dst_up == 2 and op.dst_phase >= 0)
+    assert n_phase == (12 if "deconv" in case else 0)
+
+
+def test_conv_transpose_phase_lowering_matches_torch():
+    """lower_conv_transpose on its own: every phase window / padding against F.conv_transpose2d, k = 3 and 4."""
+    import torch.nn.functional as F
+    from centernet_lightning_b200.plan import Plan, lower_conv_transpose
+    g = torch.Generator().manual_seed(0)
+    for k in (3, 4):
+        w = torch.randn((64, 64, k, k), generator=g) * 0.1
+        x = torch.randn((2, 64, 5, 7), generator=g)
+        op_pad = k % 2
+        ref = F.conv_transpose2d(x, w, None, stride=2, padding=(k + op_pad) // 2 - 1, output_padding=op_pad)
+        pl = Plan()
+        pl.add_buffer("image", 3, 1, fp32_nchw=True)
+        pl.add_buffer("src", 64, 2)
+        pl.add_buffer("dst", 64, 1)
+        pl.ops = lower_conv_transpose("up", "src", "dst", w, None, relu=False)
+        pl.outputs = {"y": "dst"}
+        out = run_plan(pl, torch.zeros(1), extra={"src": x})["y"]
+        np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=0, atol=1e-5)

@@ -14,9 +14,10 @@ from centernet_lightning_b200.plan import Plan, ConvOp  # noqa: E402
 
 
 def cfg(name, cin, cout, k, stride, hw, n=2, relu=True, res=0, precision=0, nchw=False, src_c=None, src_off=0, dst_c=None,
-        dst_off=0):
+        dst_off=0, up=0, deconv=0):
+    """up=1: conv + nearest x2 (upsampling store); deconv=k: ConvTranspose2d(k, stride 2) as four sub-pixel phase convs."""
     return dict(name=name, cin=cin, cout=cout, k=k, stride=stride, hw=hw, n=n, relu=relu, res=res, precision=precision,
-                nchw=nchw, src_c=src_c or cin, src_off=src_off, dst_c=dst_c or cout, dst_off=dst_off)
+                nchw=nchw, src_c=src_c or cin, src_off=src_off, dst_c=dst_c or cout, dst_off=dst_off, up=up, deconv=deconv)
 
 
 PROBES = [
@@ -42,6 +43,12 @@ PROBES = [
     cfg("3x3_256_256_w256_split", 256, 256, 3, 1, 256, n=1),
     cfg("3x3_64_64_w272_split", 64, 64, 3, 1, (32, 272), n=1),
     cfg("3x3_256_256_w128_fast", 256, 256, 3, 1, 128, n=1, precision=1),
+    cfg("3x3_512_256_up2_w16_split", 512, 256, 3, 1, 16, up=1),
+    cfg("3x3_128_64_up2_w64_split", 128, 64, 3, 1, 64, up=1),
+    cfg("3x3_64_64_up2_w24x40_split", 64, 64, 3, 1, (24, 40), n=1, up=1),
+    cfg("deconv3_256_w16_split", 256, 256, 3, 1, 16, deconv=3),
+    cfg("deconv4_64_w64_split", 64, 64, 4, 1, 64, deconv=4),
+    cfg("deconv4_128_w24x40_split", 128, 128, 4, 1, (24, 40), n=1, deconv=4),
 ]
 
 
@@ -63,10 +70,21 @@ def run(c, device="cuda:0", verbose=True):
         p.add_buffer("res", c["cout"], f * c["stride"] * c["res"])
         res_name = "res"
     k = c["k"]
-    w = torch.randn((c["cout"], c["cin"], k, k), generator=g) * (2.0 / (c["cin"] * k * k)) ** 0.5
+    up = 2 if (c["up"] or c["deconv"]) else 1
+    if up == 2:
+        p.buffers["dst"].stride = f // 2                # destination at twice the conv's resolution
     b = torch.randn((c["cout"],), generator=g) * 0.1
-    p.ops.append(ConvOp("probe", "conv", "src", "dst", c["cin"], c["cout"], k, c["stride"], k // 2, w, b, relu=c["relu"],
-                        src_c_off=c["src_off"], dst_c_off=c["dst_off"], residual=res_name, residual_up=max(1, c["res"])))
+    if c["deconv"]:
+        from centernet_lightning_b200.plan import lower_conv_transpose
+        w = torch.randn((c["cin"], c["cout"], k, k), generator=g) * (8.0 / (c["cin"] * k * k)) ** 0.5
+        p.ops = lower_conv_transpose("probe", "src", "dst", w, None, relu=c["relu"])
+        for op in p.ops:
+            op.bias = b
+    else:
+        w = torch.randn((c["cout"], c["cin"], k, k), generator=g) * (2.0 / (c["cin"] * k * k)) ** 0.5
+        p.ops.append(ConvOp("probe", "conv", "src", "dst", c["cin"], c["cout"], k, c["stride"], k // 2, w, b, relu=c["relu"],
+                            src_c_off=c["src_off"], dst_c_off=c["dst_off"], residual=res_name, residual_up=max(1, c["res"]),
+                            dst_up=up, dst_phase=-1))
     p.outputs = {}
     dev = torch.device(device)
     eng = Engine(p, c["n"], H, W, dev, precision=c["precision"])
@@ -77,7 +95,7 @@ def run(c, device="cuda:0", verbose=True):
         r = torch.randn((c["n"], c["cout"], oh // c["res"], ow // c["res"]), generator=g)
         eng.write_buffer("res", r)
     if not c["nchw"]:
-        eng.write_buffer("dst", torch.full((c["n"], c["dst_c"], oh, ow), 7.0))      # sentinel: untouched channels must survive
+        eng.write_buffer("dst", torch.full((c["n"], c["dst_c"], oh * up, ow * up), 7.0))      # sentinel: untouched channels must survive
     eng.forward(None)
     torch.cuda.synchronize()
     got = eng.read_buffer("dst").cpu()
@@ -86,7 +104,14 @@ def run(c, device="cuda:0", verbose=True):
         hi = t.half().float()
         return hi if c["precision"] == 1 else hi + (t - hi).half().float()
     xin = q(x)[:, c["src_off"]:c["src_off"] + c["cin"]].double()
-    ref = F.conv2d(xin, w.double(), None, c["stride"], k // 2) + b.double().view(1, -1, 1, 1)
+    if c["deconv"]:
+        op_pad = k % 2
+        ref = F.conv_transpose2d(xin, w.double(), None, stride=2, padding=(k + op_pad) // 2 - 1, output_padding=op_pad)
+        ref = ref + b.double().view(1, -1, 1, 1)
+    else:
+        ref = F.conv2d(xin, w.double(), None, c["stride"], k // 2) + b.double().view(1, -1, 1, 1)
+    if c["up"]:
+        ref = F.interpolate(ref, scale_factor=2.0, mode="nearest")
     if r is not None:
         rr = q(r).double()
         if c["res"] == 2:
