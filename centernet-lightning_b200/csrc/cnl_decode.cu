@@ -70,6 +70,20 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 constexpr int kHistBins = 4096;             // per-image histogram of candidate keys (top 12 bits), built by kernel 1
 constexpr int kHistShift = 20;
 
+// Histogram update of one candidate per lane (whole warp, converged).  Pixels without any peak keep the initial value
+// (-inf / 0): they are NOT counted - smooth maps have thousands of them per image and they would all hit one address;
+// the select kernel recovers their number as H*W minus the histogram total.  The remaining lanes are aggregated per
+// bin with match.any, so a warp issues one atomic per distinct bin.
+template <bool LOGITS>
+__device__ __forceinline__ void hist_add(unsigned int* hist_img, float v, bool valid) {
+  const bool counted = valid && (LOGITS ? (v != -INFINITY) : (v != 0.0f));
+  const uint32_t bin = sortable_key(v) >> kHistShift;
+  const unsigned peers = __match_any_sync(0xffffffffu, counted ? bin : 0xffffffffu);
+  if (counted && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist_img + bin, (unsigned)__popc(peers));
+}
+// bin that holds the uncounted "no peak" candidates
+__host__ __device__ constexpr int no_peak_bin(bool logits) { return logits ? 7 : 2048; }   // key(-inf) = 0x007fffff, key(0.f) = 0x80000000
+
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1a: fast streaming peaks kernel (W % 4 == 0).  One warp = RxTW pixel strip x one class group.
 // ------------------------------------------------------------------------------------------------------------
@@ -258,13 +272,12 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uin
             make_float4(best[i][4 * u], best[i][4 * u + 1], best[i][4 * u + 2], best[i][4 * u + 3]);
     __syncthreads();
   }
-  for (int i = g; i < R; i += G) {          // warp g finishes rows g, g+G, ...
-    int r = r0 + i;
-    if (r >= H) continue;
+  for (int i = g; i < R; i += G) {          // warp g finishes rows g, g+G, ...  (warp-uniform trip count)
+    const int r = r0 + i;
 #pragma unroll
     for (int u = 0; u < VEC; ++u) {
       const int xu = x0 + 4 * u;
-      if (xu >= W) continue;
+      const bool ok = (r < H) && (xu < W);
       float bv[4];
       uint32_t grp = 0;                      // which class group attained the maximum (first group on ties), 8 bits per pixel
 #pragma unroll
@@ -279,10 +292,12 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uin
         } else {
           bv[j] = best[i][4 * u + j];
         }
-        atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(bv[j]) >> kHistShift), 1u);
+        hist_add<LOGITS>(hist + (size_t)n * kHistBins, bv[j], ok);
       }
-      *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + xu) = grp;
-      *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + xu) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      if (ok) {
+        *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + xu) = grp;
+        *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + xu) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      }
     }
   }
 }
@@ -410,7 +425,7 @@ peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __re
         bv[j] = s_v[0][i][lane * 4 + j];
 #pragma unroll
         for (int gg = 1; gg < G; ++gg) bv[j] = fmaxf(bv[j], s_v[gg][i][lane * 4 + j]);
-        atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(bv[j]) >> kHistShift), 1u);
+        hist_add<LOGITS>(hist + (size_t)n * kHistBins, bv[j], true);
       }
       *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + x0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
       *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + x0) = 0xffffffffu;   // classes interleaved: scan all
@@ -445,7 +460,8 @@ peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cbest, 
   }
   cbest[(size_t)n * plane + (size_t)y * W + x] = best;
   cgroup[(size_t)n * plane + (size_t)y * W + x] = 0xff;
-  atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(best) >> kHistShift), 1u);
+  if (LOGITS ? (best != -INFINITY) : (best != 0.0f))          // no-peak pixels are not counted (see hist_add)
+    atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(best) >> kHistShift), 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -742,8 +758,19 @@ select_gather_kernel(DecodeParams p) {
 
   // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
   const uint4 h4 = *reinterpret_cast<const uint4*>(p.hist + (size_t)n * kHistBins + (kHistBins - 4 - 4 * tid));
-  const int cnt[4] = {(int)h4.w, (int)h4.z, (int)h4.y, (int)h4.x};      // descending bin order
-  const int sum4 = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  int cnt[4] = {(int)h4.w, (int)h4.z, (int)h4.y, (int)h4.x};            // descending bin order
+  int sum4 = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  {
+    // pixels without a peak were not counted by kernel 1 (hist_add): they all sit in one known bin
+    const int total = block_inclusive_scan(sum4, s_warp);      // inclusive -> last thread holds the sum
+    __shared__ int s_total;
+    if (tid == kSelThreads - 1) s_total = total;
+    __syncthreads();
+    const int missing = HW - s_total;
+    const int nb = no_peak_bin(p.from_logits != 0);
+    const int owner = (kHistBins - 1 - nb) >> 2, slot = (kHistBins - 1 - nb) & 3;            // thread / position of that bin
+    if (tid == owner) { cnt[slot] += missing; sum4 += missing; }
+  }
   int incl = block_inclusive_scan(sum4, s_warp);
   int run = incl - sum4;
   if (run < k && k <= incl) {                    // exactly one thread: the k-th largest lies in one of its bins
