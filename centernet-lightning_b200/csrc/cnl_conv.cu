@@ -670,7 +670,9 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   if (op.up == 2 && (d.dst_phase < -1 || d.dst_phase > 3)) return fail(CNL_ERR_INVALID_ARGUMENT, "conv dst_phase %d", d.dst_phase);
   if (op.up == 2 && (dst.fp32_nchw || d.residual >= 0)) return fail(CNL_ERR_UNSUPPORTED, "an upsampling store needs an NHWC destination and no residual");
   if (src.h / d.stride * op.up != dst.h || src.w / d.stride * op.up != dst.w) return fail(CNL_ERR_INVALID_ARGUMENT, "conv output size mismatch");
-  if (d.cout % 256 == 0) { op.n_tile = 256; op.cout_pad = d.cout; }
+  static const int env_ntile = [] { const char* v = getenv("CNL_NTILE"); return v ? atoi(v) : 0; }();
+  if (env_ntile == 128 && d.cout % 128 == 0 && d.cout > 128 && !dst.fp32_nchw) { op.n_tile = 128; op.cout_pad = d.cout; }   // experiment
+  else if (d.cout % 256 == 0) { op.n_tile = 256; op.cout_pad = d.cout; }
   else if (d.cout <= 256) { op.cout_pad = (d.cout + 15) / 16 * 16; op.n_tile = op.cout_pad; }
   else return fail(CNL_ERR_UNSUPPORTED, "conv Cout=%d (must be <= 256 or a multiple of 256)", d.cout);
   op.n_tiles = op.cout_pad / op.n_tile;

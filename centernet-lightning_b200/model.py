@@ -377,9 +377,10 @@ class CenterNet(nn.Module):
     # ---- folder inference (reference README.md:49-65) ------------------------------------------------------
     @torch.no_grad()
     def inference_detection(self, img_dir: str, img_names: Optional[Sequence[str]] = None, batch_size: int = 4,
-                            num_detections: Optional[int] = None, img_size: int = 512, device: str = "cuda:0"):
+                            num_detections: Optional[int] = None, img_size: int = 512, device: str = "cuda:0",
+                            workers: Optional[int] = None):
         from .inference import run_folder
-        return run_folder(self, img_dir, img_names, batch_size, num_detections, img_size, torch.device(device))
+        return run_folder(self, img_dir, img_names, batch_size, num_detections, img_size, torch.device(device), workers)
 
 
 def _unpack(heatmap, box_2d, reid):

@@ -75,6 +75,14 @@ int cnl_sigmoid(const float* in, float* out, size_t n, void* stream);
  * detections to the COCO evaluator (centernet_lightning/models/centernet.py:207).  In-place allowed. */
 int cnl_boxes_xyxy_to_xywh(const float* boxes_xyxy, float* boxes_xywh, size_t n_boxes, void* stream);
 
+/* Input side of the path: n uint8 RGB images in HWC order (cv2.imread + cvtColor + cv2.resize of the reference's
+ * InferenceDataset, centernet_lightning/datasets/inference.py:28-33) -> normalised fp32 NCHW, with the arithmetic
+ * of albumentations.Normalize as the reference applies it (README.md:84-87): out = float(double(x) - mean255[c]) *
+ * inv_std255[c], mean255 = mean*255 (double), inv_std255 = float(1/(std*255)).  mean255 / inv_std255 are HOST
+ * pointers to 3 values; images are device pointers. */
+int cnl_normalize_images_u8(const uint8_t* images_hwc, float* images_nchw, int n, int h, int w,
+                            const double* mean255, const float* inv_std255, void* stream);
+
 /* Stand-alone box gather for caller-supplied indices: CenterNet.gather_and_decode_boxes
  * (centernet_lightning/models/centernet.py:263-304, a staticmethod the reference also calls from its
  * loss, :162-165).  indices (N,k) int64 device; boxes (N,k,4) f32, 16-byte aligned.  Out-of-range

@@ -239,6 +239,56 @@ def test_inference_detection_folder(cuda, tmp_path):
     np.testing.assert_allclose(one["scores"][0], out["scores"][3], rtol=0, atol=1e-6)
 
 
+def test_normalize_u8_bit_exact(cuda):
+    """csrc/cnl_io.cu vs the numpy arithmetic of A.Normalize (oracle/preprocess_np.py): bit-exact, every byte value,
+    vectorised (W % 4 == 0) and scalar (odd W) kernels, default and custom statistics."""
+    from centernet_lightning_b200 import preprocess
+    from oracle import preprocess_np
+    rng = np.random.default_rng(3)
+    for shape in [(2, 32, 64, 3), (3, 17, 23, 3), (1, 16, 16, 3)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        img.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)
+        for mean, std in [(preprocess_np.MEAN, preprocess_np.STD), ((0.5, 0.5, 0.5), (0.5, 0.25, 1.0))]:
+            got = preprocess.normalize_u8(torch.from_numpy(img).to(cuda), mean=mean, std=std).cpu().numpy()
+            ref = np.stack([preprocess_np.to_chw(preprocess_np.normalize(im, mean, std)) for im in img])
+            assert got.dtype == np.float32 and got.shape == ref.shape
+            assert np.array_equal(got, ref)
+    with pytest.raises(ValueError):
+        preprocess.normalize_u8(torch.zeros((1, 4, 4, 4), dtype=torch.uint8, device=cuda))
+    with pytest.raises(RuntimeError):
+        preprocess.normalize_u8(torch.zeros((1, 4, 4, 3), dtype=torch.uint8))
+
+
+def test_inference_detection_equals_detect_on_oracle_preprocessed_images(cuda, tmp_path):
+    """The threaded uint8 loader + GPU normalisation feed the model the same tensor as the reference's CPU transform
+    (oracle/preprocess_np.py), so folder inference returns exactly what detect() returns on those tensors; a partial
+    last batch and a multi-batch folder are covered (7 images, batch 3)."""
+    import cv2
+    from centernet_lightning_b200.model import CenterNet
+    from oracle import preprocess_np
+    rng = np.random.default_rng(1)
+    names = []
+    for i in range(7):
+        im = rng.integers(0, 255, (40 + 16 * i, 96 - 8 * i, 3), dtype=np.uint8)
+        name = f"f{i:02d}.{'jpg' if i % 2 else 'png'}"
+        cv2.imwrite(str(tmp_path / name), im)
+        names.append(name)
+    net = CenterNet(80, box_multiplier=16.0).init_synthetic_(2).to(cuda)
+    out = net.inference_detection(str(tmp_path), batch_size=3, num_detections=30, img_size=128, workers=4)
+    assert out["bboxes"].shape == (7, 30, 4)
+    x = np.stack([preprocess_np.to_chw(preprocess_np.normalize(preprocess_np.load_resized_u8(str(tmp_path / n), 128))) for n in sorted(names)])
+    x = np.concatenate([x, np.zeros((2, 3, 128, 128), np.float32)])           # pad to 3 batches of 3
+    net.hparams.num_detections = 30
+    for b in range(3):
+        det = net.detect(torch.from_numpy(x[3 * b:3 * b + 3]).to(cuda))
+        m = min(3, 7 - 3 * b)
+        assert np.array_equal(det["boxes"][:m].cpu().numpy(), out["bboxes"][3 * b:3 * b + m])
+        assert np.array_equal(det["labels"][:m].cpu().numpy(), out["labels"][3 * b:3 * b + m])
+        assert np.array_equal(det["scores"][:m].cpu().numpy(), out["scores"][3 * b:3 * b + m])
+    with pytest.raises(FileNotFoundError):
+        net.inference_detection(str(tmp_path / "missing"))
+
+
 def test_small_variant_resnet18_fpn128_heads128x2(cuda):
     """The other published variant (reference docs/experiments.md:24: FPN dim 128, heads w128 d2) on a ResNet-18 trunk
     (reference tests/test_models.py:37 lists resnet18): exercises Cout tiles of 128 and a 2-deep tower."""

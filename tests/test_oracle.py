@@ -117,3 +117,19 @@ def test_simple_neck_shape_contract():
     with torch.no_grad():
         y = nk([torch.rand(4, 512, 16, 16)])
     assert tuple(y.shape) == (4, 64, 128, 128) and nk.stride == 8
+
+
+def test_preprocess_oracle_properties():
+    """oracle/preprocess_np.py (A.Normalize restated): float32 output, exact for the documented formula, affine and
+    monotone per channel, and equal to the textbook (x/255 - mean)/std within 2 ulp."""
+    from oracle import preprocess_np
+    img = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, axis=2)
+    out = preprocess_np.normalize(img)
+    assert out.dtype == np.float32 and out.shape == (16, 16, 3)
+    for c in range(3):
+        col = out[..., c].reshape(-1)
+        assert np.all(np.diff(col) > 0)
+        textbook = (np.arange(256) / 255.0 - preprocess_np.MEAN[c]) / preprocess_np.STD[c]
+        np.testing.assert_allclose(col, textbook, rtol=3e-7, atol=3e-7)
+    chw = preprocess_np.to_chw(out)
+    assert chw.shape == (3, 16, 16) and chw.flags["C_CONTIGUOUS"]
