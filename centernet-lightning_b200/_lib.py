@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CNL_LIB") or os.path.join(_HERE, "libcnl_b200.so")
 EXPORTS = (
     "cnl_last_error", "cnl_version", "cnl_compiled_sm",
     "cnl_decode_workspace_bytes", "cnl_decode_detections", "cnl_gather_boxes", "cnl_sigmoid", "cnl_boxes_xyxy_to_xywh",
-    "cnl_normalize_images_u8",
+    "cnl_normalize_images_u8", "cnl_track_workspace_bytes", "cnl_track_cost_matrices",
     "cnl_engine_create", "cnl_engine_destroy", "cnl_engine_arena_bytes", "cnl_engine_buffer_offset",
     "cnl_engine_upload", "cnl_engine_forward", "cnl_engine_read_buffer", "cnl_engine_write_buffer",
 )
@@ -67,6 +67,11 @@ def load() -> C.CDLL:
     lib.cnl_normalize_images_u8.restype = C.c_int
     lib.cnl_normalize_images_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
                                             C.POINTER(C.c_float), C.c_void_p]
+    lib.cnl_track_workspace_bytes.restype = C.c_size_t
+    lib.cnl_track_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    lib.cnl_track_cost_matrices.restype = C.c_int
+    lib.cnl_track_cost_matrices.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cnl_gather_boxes.restype = C.c_int
     lib.cnl_gather_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_float, C.c_int, C.c_void_p, C.c_void_p]

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcnl_b200.so")
-SOURCES = ["cnl_decode.cu", "cnl_conv.cu", "cnl_io.cu"]
+SOURCES = ["cnl_decode.cu", "cnl_conv.cu", "cnl_io.cu", "cnl_track.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

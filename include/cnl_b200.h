@@ -91,6 +91,19 @@ int cnl_gather_boxes(const float* box_offsets, const int64_t* indices, int n, in
                      int normalize_boxes, int box_log, float box_multiplier, int stride,
                      float* boxes, void* stream);
 
+/* Tracker association costs for one frame (the consumer of the tracking head's detections):
+ *   reid_cost[i][j] = scipy.spatial.distance.cdist(det_emb, trk_emb, "cosine")   (centernet_lightning/models/tracker.py:61,157)
+ *   box_cost[i][j]  = 1 - IoU (giou = 0) or 1 - GIoU (giou = 1) of xyxy boxes    (centernet_lightning/utils/box.py:49-92,
+ *                                                                                 tracker.py:63,169)
+ * All arrays are device pointers, row-major float64: det_emb (n_det, emb_dim), trk_emb (n_trk, emb_dim), det_box (n_det, 4),
+ * trk_box (n_trk, 4), outputs (n_det, n_trk).  Either pair (embeddings + reid_cost / boxes + box_cost) may be NULL.
+ * fp64 with the host code's operation order: equal to scipy / numpy float64 results to the last bit.  The Hungarian
+ * assignment (tracker.py:28) stays on the host. */
+size_t cnl_track_workspace_bytes(int n_det, int n_trk);
+int cnl_track_cost_matrices(const double* det_emb, const double* trk_emb, int emb_dim,
+                            const double* det_box, const double* trk_box, int n_det, int n_trk, int giou,
+                            double* reid_cost, double* box_cost, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Forward: backbone -> neck -> heads as a list of fused convolution launches.
  *

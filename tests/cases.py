@@ -78,3 +78,53 @@ FORWARD_CASES = {
 def make_image(kw):
     g = torch.Generator().manual_seed(kw["img_seed"])
     return torch.rand((kw["n"], 3, kw["size"], kw["size"]), generator=g)
+
+
+# ---- tracker sequences: seeded detection streams for Tracker.update --------------------------------
+TRACK_CASES = {
+    "walk_iou": dict(seed=0, frames=40, objects=6, dim=64, tracker=dict(box_cost="iou")),
+    "walk_giou": dict(seed=1, frames=40, objects=8, dim=64, tracker=dict(box_cost="giou", reid_threshold=0.3)),
+    "reid_only": dict(seed=2, frames=30, objects=5, dim=16, tracker=dict(box_cost=None, min_birth_age=1, max_inactive_age=3)),
+    "crowded": dict(seed=3, frames=25, objects=20, dim=64, tracker=dict(detection_threshold=0.4, smoothing_factor=0.9)),
+}
+
+
+def make_track_sequence(case):
+    """List of per-frame (bboxes (k,4) f32 normalised xyxy, labels (k,) i64, scores (k,) f32 descending, embeddings (k,E) f32):
+    objects drift with constant velocity, are missed at random, and false positives with random appearance are mixed in."""
+    import numpy as np
+    rng = np.random.default_rng(case["seed"])
+    m, e = case["objects"], case["dim"]
+    centre = rng.uniform(0.2, 0.8, (m, 2))
+    vel = rng.normal(0, 0.006, (m, 2))
+    size = rng.uniform(0.05, 0.15, (m, 2))
+    ident = rng.standard_normal((m, e))
+    frames = []
+    for _ in range(case["frames"]):
+        centre = centre + vel
+        seen = rng.random(m) > 0.15
+        boxes = np.concatenate([centre - size / 2, centre + size / 2], axis=1)[seen] + rng.normal(0, 0.003, (int(seen.sum()), 4))
+        emb = (ident + 0.15 * rng.standard_normal((m, e)))[seen] * rng.uniform(0.5, 2.0, (int(seen.sum()), 1))
+        score = rng.uniform(0.35, 0.95, int(seen.sum()))
+        n_fp = int(rng.integers(0, 4))
+        fc = rng.uniform(0.1, 0.9, (n_fp, 2))
+        fs = rng.uniform(0.03, 0.1, (n_fp, 2))
+        boxes = np.concatenate([boxes, np.concatenate([fc - fs / 2, fc + fs / 2], axis=1)])
+        emb = np.concatenate([emb, rng.standard_normal((n_fp, e))])
+        score = np.concatenate([score, rng.uniform(0.05, 0.6, n_fp)])
+        order = np.argsort(-score, kind="stable")                  # gather_tracking2d returns detections sorted by score
+        frames.append((boxes[order].astype(np.float32), np.zeros(len(order), np.int64), score[order].astype(np.float32),
+                       emb[order].astype(np.float32)))
+    return frames
+
+
+def run_track_sequence(tracker, frames):
+    """Feeds the frames to ``tracker.update`` and records, per frame, every live track: (frame, track_id, state value,
+    bbox) rows - the observable behaviour of the association."""
+    import numpy as np
+    rows = []
+    for f, (b, l, s, e) in enumerate(frames):
+        tracker.update(b, l, s, e)
+        for t in tracker.tracks:
+            rows.append([f, t.track_id, t.state.value, *np.asarray(t.bbox, dtype=np.float64).tolist()])
+    return np.array(rows, dtype=np.float64)

@@ -10,6 +10,9 @@ from the seeded recipe in tests/cases.py, so each file holds only the small outp
 Forward golden: the reference's own ``GenericModel`` + ``GenericHead`` (reference models/meta.py:21-47)
 wrapped around the in-repo backbone/neck stand-ins (vision_toolbox is not vendored), on a
 64x64 seeded image - pins the wiring of the spec model and gives the GPU engine a value-level target.
+
+Tracker goldens: the reference's own ``Tracker`` (reference models/tracker.py, loaded by oracle/tracker_np.py) driven
+through ``update`` with seeded detection streams; every live track of every frame is recorded.
 """
 import os
 import sys
@@ -21,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from oracle import ref_import, spec_model  # noqa: E402
+from oracle import ref_import, spec_model, tracker_np  # noqa: E402
 import cases  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -48,6 +51,18 @@ def main():
             out = rm(x)
         np.savez_compressed(os.path.join(HERE, f"forward_{name}.npz"), **{k: v.numpy() for k, v in out.items()})
         print("forward", name, {k: tuple(v.shape) for k, v in out.items()})
+
+    # tracker goldens: the reference's own Tracker.update (models/tracker.py:131-201, scipy cdist + utils/box.py costs,
+    # scipy Hungarian) on the seeded detection streams of tests/cases.py; rows = (frame, track_id, state, bbox)
+    ref_trk = tracker_np.import_reference_tracker()
+    import warnings
+    for name, case in cases.TRACK_CASES.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t = ref_trk.Tracker(model=None, **case["tracker"])
+        rows = cases.run_track_sequence(t, cases.make_track_sequence(case))
+        np.savez_compressed(os.path.join(HERE, f"tracker_{name}.npz"), rows=rows, next_track_id=np.array(t.next_track_id))
+        print("tracker", name, rows.shape, "tracks created:", t.next_track_id)
 
 
 if __name__ == "__main__":
