@@ -69,6 +69,10 @@ struct ConvParams {
   int dst_phase;                // dst_up == 2: -1 = write every pixel to its whole 2x2 block (conv + nearest x2 upsample),
                                 //              0..3 = write only sub-pixel (py, px) = (phase >> 1, phase & 1)
   int dst_c;                    // channels of the destination buffer (dst_up == 2: sub-pixel px is folded into dim 0)
+  // ROWS mode (see conv_tc_kernel): input rows live in a ring of shared-memory slots and are reused by every tap
+  int a_slots;                  // row slots in the ring (>= kh + 1)
+  int a_slot_bytes;             // bytes of one slot and plane: (tw + kw - 1) pixels x 128 B, rounded up to 1024
+  int box_w;                    // pixels per loaded row: tw + kw - 1
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -82,7 +86,16 @@ struct ConvParams {
 //
 // Epilogue: 8 warps.  Warps w and w+4 own the same TMEM lane quarter (w & 3) and split the tile's columns in halves,
 // so two tcgen05.ld -> convert -> store chains per scheduler overlap their latencies.
-template <int NPLANE, bool CORR>
+//
+// ROWS = true ("row-rolling", stride-1 convs with Cin = 64 on maps at least 65 pixels wide, i.e. one output row of 128
+// pixels per tile): the im2col view re-reads every input pixel once per tap - 9x for a 3x3 conv - and for Cin = Cout = 64
+// that L2 -> shared-memory traffic (432 KB per 128-pixel tile), not the tensor pipe or HBM, bounds the kernel.  Here a
+// CTA owns a run of consecutive output rows of one image column strip and keeps the last kh input rows (each tw + kw - 1
+// pixels, both planes) in a ring of shared-memory slots; every output row needs ONE new input row.  The A operand of
+// tap (r, s) is a shifted view of a slot: start address = slot of input row (h + r - pad_h) + s pixels x 128 B - the
+// 128-byte swizzle is a function of the shared-memory address bits, so a view that starts s rows into a swizzle atom reads
+// exactly what TMA wrote there.  Only the weight tiles still stream through the stage ring.
+template <int NPLANE, bool CORR, bool ROWS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap w_map,
                const __grid_constant__ CUtensorMap dst_map, const ConvParams p) {
@@ -91,6 +104,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t a_full_bar[kMaxStages];       // ROWS: input-row slots
+  __shared__ __align__(8) uint64_t a_empty_bar[kMaxStages];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -98,8 +113,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const int b_tile_bytes = p.n_tile * kBlockK * 2;
-  const int stage_bytes = NPLANE * (kATileBytes + b_tile_bytes);
-  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;        // [8 warps][NPLANE][2048], 1024-aligned
+  const int stage_bytes = ROWS ? NPLANE * b_tile_bytes : NPLANE * (kATileBytes + b_tile_bytes);   // ROWS: stages hold weights only
+  const int a_ring_bytes = ROWS ? p.a_slots * NPLANE * p.a_slot_bytes : 0;
+  uint8_t* a_ring = smem;                                               // ROWS: [a_slots][NPLANE][a_slot_bytes]
+  uint8_t* stages = smem + a_ring_bytes;
+  uint8_t* staging = stages + (size_t)p.num_stages * stage_bytes;      // [8 warps][NPLANE][2048], 1024-aligned
   const int taps = p.kh * p.kw;
   const int k_iters = taps * p.kblocks;
 
@@ -109,6 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     if (p.out_mode == 0) ptx::prefetch_tmap(&dst_map);
     for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], p.cluster); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps); }
+    if (ROWS) for (int i = 0; i < p.a_slots; ++i) { ptx::mbar_init(&a_full_bar[i], 1); ptx::mbar_init(&a_empty_bar[i], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -119,6 +138,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   __syncthreads();
   if (p.cluster > 1) ptx::cluster_sync_all();       // peers' barriers are initialised before any multicast / remote arrive
   ptx::tc_fence_after();
+  // Programmatic dependent launch: this CTA became resident as soon as an SM of the previous launch drained, and its
+  // set-up above (tensor-map prefetch, barrier init, TMEM allocation) overlapped that launch's tail.  Everything the
+  // previous launch wrote (this op's input, residual) is visible only after the wait.  No activation buffer is ever
+  // rewritten inside one forward, so there is no write-after-read hazard to order.
+  ptx::grid_dependents_launch();
+  ptx::grid_dependency_wait();
   const uint32_t tmem_base = tmem_base_smem;
   // Work distribution.  A cluster of `csize` CTAs takes `csize` consecutive pixel tiles of the SAME Cout tile, so the
   // weight tile is fetched from L2 once per cluster: CTA r loads rows [r, r+1) * n_tile/csize and multicasts them.
@@ -132,10 +157,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const bool two_acc = p.acc_stages == 2;
+  // ROWS: tiles are numbered (image, column strip, row) and every CTA takes one contiguous run of them
+  const int rows_t0 = ROWS ? (int)((long long)p.m_tiles * blockIdx.x / gridDim.x) : 0;
+  const int rows_t1 = ROWS ? (int)((long long)p.m_tiles * (blockIdx.x + 1) / gridDim.x) : 0;
 
   if (warp == 0) {
     // ===================================== TMA producer ==============================================
-    if (lane == 0) {
+    if (ROWS && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int n_loads = 0;                                     // input rows loaded so far (slot = n_loads % a_slots)
+      const int row_bytes = p.box_w * kBlockK * 2;
+      for (int t = rows_t0; t < rows_t1; ++t) {
+        const int strip = t / p.tiles_h, h = t - strip * p.tiles_h;
+        const int img = strip / p.tiles_w, w0 = (strip - img * p.tiles_w) * p.tw;
+        const bool fresh = (t == rows_t0) || (h == 0);     // first output row of this CTA's run or of a new strip
+        const int n_new = fresh ? p.kh : 1;
+        for (int q = 0; q < n_new; ++q, ++n_loads) {
+          const int in_row = h - p.pad_h + (fresh ? q : p.kh - 1);
+          const int slot = n_loads % p.a_slots;
+          ptx::mbar_wait(&a_empty_bar[slot], ((n_loads / p.a_slots) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&a_full_bar[slot], NPLANE * row_bytes);
+#pragma unroll
+          for (int pl = 0; pl < NPLANE; ++pl)
+            ptx::tma_load_4d(a_ring + ((size_t)slot * NPLANE + pl) * p.a_slot_bytes, &src_map, &a_full_bar[slot], p.src_c_off,
+                             w0 - p.pad_w, in_row, img + pl * p.n_img);
+        }
+        for (int tap = 0; tap < taps; ++tap) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* st = stages + (size_t)stage * stage_bytes;
+#pragma unroll
+          for (int pl = 0; pl < NPLANE; ++pl)
+            ptx::tma_load_3d(st + pl * b_tile_bytes, &w_map, &full_bar[stage], 0, 0, tap + pl * taps);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    if (!ROWS && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.n_tile / csize;
@@ -154,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            uint8_t* st = smem + (size_t)stage * stage_bytes;
+            uint8_t* st = stages + (size_t)stage * stage_bytes;
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl)
               ptx::tma_load_4d(st + pl * kATileBytes, &src_map, &full_bar[stage], p.src_c_off + kb * kBlockK, cw, ch,
@@ -177,7 +236,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =================================================
-    if (lane == 0) {
+    if (ROWS && lane == 0) {
+      // row-rolling issue loop: always the cat form (N = 2*n_tile for hi x [hi|lo], N = n_tile for lo x hi)
+      const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
+      const uint32_t idesc_cat = ptx::make_idesc_f16_m128((uint32_t)p.n_tile * 2u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int n_loads = 0, acc_it = 0;
+      for (int t = rows_t0; t < rows_t1; ++t, ++acc_it) {
+        const int h = t % p.tiles_h;
+        const bool fresh = (t == rows_t0) || (h == 0);
+        const bool last = (t + 1 == rows_t1) || (h == p.tiles_h - 1);   // the rows in the ring die with this output row
+        const int n_new = fresh ? p.kh : 1;
+        const int as = two_acc ? (acc_it & 1) : 0;
+        const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        for (int q = 0; q < n_new; ++q, ++n_loads) ptx::mbar_wait(&a_full_bar[n_loads % p.a_slots], (n_loads / p.a_slots) & 1);
+        ptx::tc_fence_after();
+        const int first_load = n_loads - p.kh;               // load index of input row h - pad_h
+        const uint32_t d_tmem = tmem_base + as * 256;
+        const uint32_t d_corr = d_tmem + p.corr_off;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.kw, sx = tap - r * p.kw;
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const int slot = (first_load + r) % p.a_slots;
+          const uint32_t a_addr = ptx::smem_u32(a_ring + (size_t)slot * NPLANE * p.a_slot_bytes) + sx * (kBlockK * 2);
+          const uint32_t b_addr = ptx::smem_u32(stages + (size_t)stage * stage_bytes);
+          // (descriptor base-offset field stays 0: measured on B200, the swizzle phase comes from the address bits)
+          const uint64_t a_hi = ptx::make_sw128_kmajor_desc(a_addr);
+          const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + p.a_slot_bytes);
+          const uint64_t b_hi = ptx::make_sw128_kmajor_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+            ptx::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, (tap | k) != 0);
+            if (NPLANE == 2) ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        // the oldest input row is not needed by the next output row; at the end of a strip / run none of them is
+        ptx::umma_commit(&a_empty_bar[first_load % p.a_slots]);
+        if (last) for (int r = 1; r < p.kh; ++r) ptx::umma_commit(&a_empty_bar[(first_load + r) % p.a_slots]);
+        ptx::umma_commit(&tmem_full_bar[as]);
+      }
+    }
+    if (!ROWS && lane == 0) {
       const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
       // cat: the hi and lo weight tiles sit back to back in the stage (n_tile rows of 128 B each, whole swizzle atoms),
       // so A_hi x [B_hi | B_lo] is ONE instruction of N = 2*n_tile whose columns [n_tile, 2*n_tile) are the correction
@@ -198,7 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         for (int it = 0; it < k_iters; ++it) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_addr = ptx::smem_u32(stages + (size_t)stage * stage_bytes);
           const uint32_t b_addr = a_addr + NPLANE * kATileBytes;
           const uint64_t a_hi = ptx::make_sw128_kmajor_desc(a_addr);
           const uint64_t b_hi = ptx::make_sw128_kmajor_desc(b_addr);
@@ -233,17 +338,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const int lane_base = q * 32;
     uint8_t* my_stage = staging + (size_t)(warp - 2) * NPLANE * kStageWarpBytes;
     int acc_it = 0;
-    for (int grp = group0; grp < total_groups; grp += group_step, ++acc_it) {
+    const int it_begin = ROWS ? rows_t0 : group0, it_end = ROWS ? rows_t1 : total_groups, it_step = ROWS ? 1 : group_step;
+    for (int grp = it_begin; grp < it_end; grp += it_step, ++acc_it) {
       const int as = two_acc ? (acc_it & 1) : 0;
       const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
-      const int n_idx = grp % p.n_tiles;
-      int m_idx = (grp / p.n_tiles) * csize + crank;
-      int img = m_idx / tiles_per_img;
-      m_idx -= img * tiles_per_img;
-      const bool dummy = img >= p.n_img;
-      if (dummy) img = 1 << 20;
-      const int h0 = (m_idx / p.tiles_w) * p.th;
-      const int w0 = (m_idx % p.tiles_w) * p.tw;
+      int n_idx, img, h0, w0;
+      bool dummy = false;
+      if (ROWS) {
+        const int strip = grp / p.tiles_h;
+        n_idx = 0;
+        h0 = grp - strip * p.tiles_h;                      // th == 1
+        img = strip / p.tiles_w;
+        w0 = (strip - img * p.tiles_w) * p.tw;
+      } else {
+        n_idx = grp % p.n_tiles;
+        int m_idx = (grp / p.n_tiles) * csize + crank;
+        img = m_idx / tiles_per_img;
+        m_idx -= img * tiles_per_img;
+        dummy = img >= p.n_img;
+        if (dummy) img = 1 << 20;
+        h0 = (m_idx / p.tiles_w) * p.th;
+        w0 = (m_idx % p.tiles_w) * p.tw;
+      }
       const int pix = lane_base + lane;
       const int h = h0 + pix / p.tw, w = w0 + pix % p.tw;
       const bool valid = !dummy && (h < p.out_h) && (w < p.out_w);
@@ -578,6 +694,7 @@ struct OpInfo {
   // conv
   int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off, cat;
   int kh, kw, pad_h, pad_w, up;         // resolved kernel extent / padding, destination scale (1 or 2)
+  int rows, a_slots, a_slot_bytes, box_w; // ROWS mode geometry (rows = 0: im2col tiles)
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
@@ -643,6 +760,17 @@ static bool cat_enabled() {
   static const bool on = [] { const char* v = getenv("CNL_CAT"); return !(v && atoi(v) == 0); }();
   return on;
 }
+
+// CNL_ROWS=0 switches the row-rolling kernel variant off (A/B timing)
+static bool rows_enabled() {
+  static const bool on = [] { const char* v = getenv("CNL_ROWS"); return !(v && atoi(v) == 0); }();
+  return on;
+}
+
+// Row-rolling geometry for an op whose tiles are single output rows (see conv_tc_kernel<.., ROWS = true>).  Returns false
+// (and leaves the im2col configuration in place) when the op does not qualify or the ring does not fit shared memory.
+struct OpInfo;
+static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhwc_out, int precision);
 
 static void split_half(float x, __half* hi, __half* lo) {
   *hi = __float2half_rn(x);
@@ -713,6 +841,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   if (op.cat) op.corr = true;
   op.corr_off = op.cat ? op.n_tile : ((op.n_tile <= 128) ? 128 : 256);
   op.acc_stages = (split_corr && op.n_tile > 128) ? 1 : 2;
+  plan_rows_mode(op, planes, d.cin, d.stride, !dst.fp32_nchw, e->precision);
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = op.kh * op.kw;
@@ -744,6 +873,26 @@ static void pack_split_weights(OpInfo& op, const std::vector<float>& w /*[cout][
       }
 }
 
+static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhwc_out, int precision) {
+  op.rows = 0; op.a_slots = 0; op.a_slot_bytes = 0; op.box_w = 0;
+  if (!rows_enabled() || precision != CNL_PRECISION_SPLIT || !op.cat || planes != 2) return false;
+  if (cin != 64 || stride != 1 || op.th != 1 || op.n_tiles != 1 || op.kh * op.kw < 2 || op.cluster != 1 || !nhwc_out) return false;
+  const int box_w = op.tw + op.kw - 1;
+  if (box_w > 256) return false;
+  const int slot_bytes = (box_w * kBlockK * 2 + 1023) / 1024 * 1024;
+  const int b_stage = planes * op.n_tile * kBlockK * 2;
+  const int staging = kEpiWarps * planes * kStageWarpBytes;
+  int slots = op.kh + 2;                                          // two rows of look-ahead when they fit, else one
+  int b_stages = (kSmemLimit - 1024 - staging - slots * planes * slot_bytes) / b_stage;
+  if (b_stages < 3) { slots = op.kh + 1; b_stages = (kSmemLimit - 1024 - staging - slots * planes * slot_bytes) / b_stage; }
+  // fewer than three weight stages in flight and the kernel waits on weight-tile latency instead (measured on the stem's
+  // 4x1 conv: 5 row slots leave room for two stages and the im2col form is faster)
+  if (b_stages < 3 || slots > kMaxStages) return false;
+  op.rows = 1; op.a_slots = slots; op.a_slot_bytes = slot_bytes; op.box_w = box_w;
+  op.num_stages = std::min(kMaxStages, b_stages);
+  return true;
+}
+
 static int prepare_stem(cnl_engine* e, OpInfo& op) {
   const cnl_conv_desc& d = op.d;
   const BufferInfo& src = e->bufs[d.src];
@@ -768,6 +917,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   op.cat = (e->precision == CNL_PRECISION_SPLIT) && cat_enabled();
   op.corr = op.cat;                        // K = 256: the correction accumulator only comes with the cat MMA
   op.corr_off = op.cat ? 64 : 128; op.acc_stages = 2;
+  plan_rows_mode(op, planes, 64, 1, true, e->precision);
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
@@ -865,9 +1015,10 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
   CNL_CUDA_CHECK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, e->device));
   if (cc_major != 10) return fail(CNL_ERR_UNSUPPORTED, "cnl_b200 kernels are built for sm_100a only (device has compute capability %d.x)", cc_major);
   e->num_sms = dev_sms;
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   uint8_t* base = static_cast<uint8_t*>(arena);
   const int planes = e->planes;
   for (OpInfo& op : e->ops) {
@@ -879,7 +1030,7 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       cuuint64_t dims[4] = {64, sw, sh, (cuuint64_t)e->batch * planes};
       cuuint64_t str[3] = {128, sw * 128, sh * sw * 128};
       cuuint32_t es[4] = {1, 1, 1, 1};
-      cuuint32_t box_in[4] = {64, (cuuint32_t)op.tw, (cuuint32_t)op.th, 1};
+      cuuint32_t box_in[4] = {64, (cuuint32_t)(op.rows ? op.box_w : op.tw), (cuuint32_t)op.th, 1};
       cuuint32_t box_out[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
       int r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str, box_in, es, "stem im2row");
       if (r) return r;
@@ -901,7 +1052,7 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
     {
       cuuint64_t dims[4] = {(cuuint64_t)src.channels, (cuuint64_t)src.w, (cuuint64_t)src.h, (cuuint64_t)e->batch * planes};
       cuuint64_t str[3] = {(cuuint64_t)src.channels * 2, (cuuint64_t)src.w * src.channels * 2, (cuuint64_t)src.h * src.w * src.channels * 2};
-      cuuint32_t box[4] = {64, (cuuint32_t)(op.tw * d.stride), (cuuint32_t)(op.th * d.stride), 1};
+      cuuint32_t box[4] = {64, (cuuint32_t)(op.rows ? op.box_w : op.tw * d.stride), (cuuint32_t)(op.th * d.stride), 1};
       cuuint32_t es[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
       int r = encode_map(&op.src_map, base + src.offset, 4, dims, str, box, es, "src");
       if (r) return r;
@@ -955,15 +1106,22 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = kSmemLimit;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    static const bool pdl = [] { const char* v = getenv("CNL_PDL"); return !(v && atoi(v) == 0); }();
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see the griddepcontrol pair in the kernel
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (e->precision == CNL_PRECISION_SPLIT && op.corr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true>, op.src_map, op.w_map, op.dst_map, p);
-    else if (e->precision == CNL_PRECISION_SPLIT)       return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false>, op.src_map, op.w_map, op.dst_map, p);
-    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false>, op.src_map, op.w_map, op.dst_map, p);
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, op.src_map, op.w_map, op.dst_map, p);
+    cfg.numAttrs = pdl ? 2 : 1;
+    if (op.rows) {
+      cfg.gridDim = dim3(std::min(p.m_tiles, e->num_sms));
+      return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, true>, op.src_map, op.w_map, op.dst_map, p);
+    }
+    if (e->precision == CNL_PRECISION_SPLIT && op.corr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, false>, op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT)       return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, op.src_map, op.w_map, op.dst_map, p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, op.src_map, op.w_map, op.dst_map, p);
   };
   for (int i = first_op; i < last_op; ++i) {
     OpInfo& op = e->ops[i];
@@ -981,6 +1139,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
     p.acc_stages = op.acc_stages; p.corr_off = op.corr_off; p.cat = op.cat;
     p.dst_up = 1; p.dst_phase = -1; p.dst_c = dst.channels;
+    p.a_slots = op.a_slots; p.a_slot_bytes = op.a_slot_bytes; p.box_w = op.box_w;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
