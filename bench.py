@@ -126,7 +126,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -246,7 +246,8 @@ def run_ours(args):
         box = eng.outputs["box_2d"]
         bufs = cdec.DecodeBuffers(BATCH_PER_GPU, SIZE // 4, SIZE // 4, TOPK, 0, dev)
         kw = dict(num_detections=TOPK, nms_kernel=3, normalize_boxes=False, box_log=False, box_multiplier=16.0, stride=4, from_logits=True)
-        heats = [heat.clone(), heat.clone()]                    # 2 x 168 MB rotate (> 126 MB L2)
+        heats = [heat.clone() for _ in range(4)]                # 4 x 168 MB rotate (>> 126 MB L2)
+        time.sleep(1.0)                                         # the kernel is timed ALONE: let the clocks recover from the power-capped conv loop above
 
         def dec_body():
             for hmap in heats:
@@ -270,9 +271,9 @@ def run_ours(args):
             dgraph.replay()
         ev1.record()
         torch.cuda.synchronize(dev)
-        d_ms = ev0.elapsed_time(ev1) / 50
+        d_ms = ev0.elapsed_time(ev1) / (25 * len(heats))
         d_bytes = BATCH_PER_GPU * (4 * CLASSES * (SIZE // 4) ** 2 + 16 * TOPK + 28 * TOPK)
-        decode_roof = {"bound": "hbm", "kernel": "whole decode: memset + peaks_fast_kernel + select_gather_kernel (CUDA-graph replay)",
+        decode_roof = {"bound": "hbm", "kernel": "whole decode: peaks_fast_kernel + select_gather_kernel (CUDA-graph replay, network's own heatmap)",
                        "achieved": d_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                        "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm, "decode_us": d_ms * 1e3,
                        "peaks_kernel_only": {"us": 36.0, "achieved": 4660.0, "frac": 0.71,
@@ -337,10 +338,30 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write banners to file descriptor 1 behind Python's back (NCCL's
+    version line, for one), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate
+    of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -564,7 +564,7 @@ __global__ void sigmoid_kernel(const float* __restrict__ in, float* __restrict__
 }
 
 struct DecodeParams {
-  const float* cscore; const unsigned int* hist;     // per-pixel best masked value (logit or probability) + its histogram
+  const float* cscore; unsigned int* hist;           // per-pixel best masked value (logit or probability) + its histogram (zeroed again by the select kernel)
   const float* heat; int C, P, from_logits;          // the head map itself: labels are recovered for the k winners only
   const uint8_t* cgroup; int group_classes;          // class group (of group_classes classes) that holds the winner; 255 = unknown
   const float* box; const float* reid;
@@ -757,7 +757,9 @@ select_gather_kernel(DecodeParams p) {
   };
 
   // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
-  const uint4 h4 = *reinterpret_cast<const uint4*>(p.hist + (size_t)n * kHistBins + (kHistBins - 4 - 4 * tid));
+  uint4* my_bins = reinterpret_cast<uint4*>(p.hist + (size_t)n * kHistBins + (kHistBins - 4 - 4 * tid));
+  const uint4 h4 = *my_bins;
+  *my_bins = make_uint4(0u, 0u, 0u, 0u);         // leave the histogram clean for the next decode on this workspace
   int cnt[4] = {(int)h4.w, (int)h4.z, (int)h4.y, (int)h4.x};            // descending bin order
   int sum4 = cnt[0] + cnt[1] + cnt[2] + cnt[3];
   {
@@ -1076,6 +1078,9 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: bad shape (%d,%d,%d,%d)", n, c, h, w);
   if (c > 65535) return fail(CNL_ERR_UNSUPPORTED, "cnl_decode_detections: more than 65535 classes");
   if ((long long)h * w > (1ll << 30)) return fail(CNL_ERR_UNSUPPORTED, "cnl_decode_detections: map too large");
+  if (from_logits & ~(1 | CNL_DECODE_WORKSPACE_CLEAN)) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: bad from_logits flags %d", from_logits);
+  const bool workspace_clean = (from_logits & CNL_DECODE_WORKSPACE_CLEAN) != 0;
+  from_logits &= 1;
   // a negative or even kernel changes the pooled map's size in the reference (F.max_pool2d would not broadcast)
   int force_generic = 0;
   if (nms_kernel < 0) { force_generic = 1; nms_kernel = -nms_kernel; }   // test hook: negative selects the generic kernel
@@ -1100,7 +1105,9 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   unsigned int* hist = static_cast<unsigned int*>(workspace);
   float* cscore = reinterpret_cast<float*>(static_cast<char*>(workspace) + hist_bytes(n));
   const int P = (nms_kernel - 1) / 2;
-  CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
+  // the select kernel zeroes the histogram after reading it, so a workspace that was last used by a completed decode of the
+  // same batch size needs no memset (CNL_DECODE_WORKSPACE_CLEAN); a fresh or foreign workspace does
+  if (!workspace_clean) CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
   uint8_t* cgroup = reinterpret_cast<uint8_t*>(static_cast<char*>(workspace) + hist_bytes(n) + score_bytes(n, h, w));
   const int group_classes = from_logits ? launch_peaks<true>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st)
                                         : launch_peaks<false>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st);

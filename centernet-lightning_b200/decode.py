@@ -57,6 +57,7 @@ class DecodeBuffers:
             self.ws = torch.empty(lib.cnl_decode_workspace_bytes(n, h, w) + 256, dtype=torch.uint8, device=device)
             off = (-self.ws.data_ptr()) % 256
             self.ws = self.ws[off:]
+        self.clean = False          # True once a decode has run on this workspace: its histogram is left zeroed (no memset needed)
 
     def as_dict(self) -> Dict[str, torch.Tensor]:
         out = {"boxes": self.boxes, "scores": self.scores, "labels": self.labels}
@@ -73,15 +74,18 @@ def decode_into(bufs: DecodeBuffers, heatmap: torch.Tensor, box_offsets: torch.T
     n, c, h, w = heatmap.shape
     if (n, h, w, num_detections) != (bufs.n, bufs.h, bufs.w, bufs.k):
         raise ValueError("DecodeBuffers were built for another shape")
+    flags = int(bool(from_logits)) | (2 if bufs.clean else 0)           # CNL_DECODE_WORKSPACE_CLEAN
+    bufs.clean = False
     st = lib.cnl_decode_detections(
         heatmap.data_ptr(), box_offsets.data_ptr(), reid.data_ptr() if reid is not None else None,
-        n, c, h, w, bufs.e if reid is not None else 0, int(bool(from_logits)), int(nms_kernel), int(num_detections),
+        n, c, h, w, bufs.e if reid is not None else 0, flags, int(nms_kernel), int(num_detections),
         int(bool(normalize_boxes)), int(bool(box_log)), float(box_multiplier), int(stride),
         bufs.boxes.data_ptr(), bufs.scores.data_ptr(), bufs.labels.data_ptr(), bufs.indices.data_ptr(),
         bufs.emb.data_ptr() if (bufs.emb is not None and reid is not None) else None,
         bufs.ws.data_ptr(), bufs.ws.numel(), torch.cuda.current_stream(heatmap.device).cuda_stream)
     _lib.check(st, "cnl_decode_detections")
-    return 3            # memset + peaks + select
+    bufs.clean = True
+    return 2 if flags & 2 else 3            # [memset +] peaks + select
 
 
 def boxes_xyxy_to_xywh(boxes: torch.Tensor) -> torch.Tensor:

@@ -59,6 +59,10 @@ int cnl_compiled_sm(void);
  * ------------------------------------------------------------------------------------------ */
 size_t cnl_decode_workspace_bytes(int n, int h, int w);
 
+/* `from_logits` may be OR-ed with CNL_DECODE_WORKSPACE_CLEAN when the workspace was last used by a COMPLETED
+ * cnl_decode_detections call with the same n (each call leaves the histogram it used zeroed); the initial memset is then
+ * skipped.  Never set it for a fresh workspace. */
+#define CNL_DECODE_WORKSPACE_CLEAN 2
 int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
                           int n, int c, int h, int w, int reid_dim,
                           int from_logits, int nms_kernel, int num_detections,
