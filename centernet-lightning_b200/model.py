@@ -374,6 +374,28 @@ class CenterNet(nn.Module):
         self.invalidate()
         return self
 
+    # ---- checkpoints -----------------------------------------------------------------------------------------
+    def load_reference_state_dict(self, state_dict: Dict[str, torch.Tensor], key_map: Optional[Dict[str, str]] = None,
+                                  strict: bool = True):
+        """Load a reference checkpoint's ``state_dict`` (Lightning layout: ``model.backbone.*``, ``model.neck.*``,
+        ``model.heads.<head>.block_<i>.*`` / ``.out_conv.*``; reference models/meta.py:26-28,36-38,92-95).
+
+        The names INSIDE ``backbone`` / ``neck`` / ``ConvBnAct`` belong to vision_toolbox, which is not part of the
+        reference snapshot; this package uses torchvision's ResNet names, ``neck.lateral.<i>``,
+        ``neck.output.<i>.{conv,bn}`` and ``block_<i>.{conv,bn}``.  ``key_map`` = ordered ``{regex: replacement}`` rules
+        (``re.sub``) applied to every key bridges a checkpoint with other inner names.  Keys of modules that do not exist
+        at inference (``fc.*``, ``classifier.*``, loss / evaluator state) are dropped; anything else that does not match
+        raises under ``strict``."""
+        import re
+        sd = {}
+        for k, v in state_dict.items():
+            for pat, rep in (key_map or {}).items():
+                k = re.sub(pat, rep, k)
+            if re.search(r"(^|\.)(fc|classifier|evaluator|loss\w*)\.", k):
+                continue
+            sd[k] = v
+        return self.load_state_dict(sd, strict=strict)
+
     # ---- folder inference (reference README.md:49-65) ------------------------------------------------------
     @torch.no_grad()
     def inference_detection(self, img_dir: str, img_names: Optional[Sequence[str]] = None, batch_size: int = 4,

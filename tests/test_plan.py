@@ -95,3 +95,30 @@ def test_conv_transpose_phase_lowering_matches_torch():
         pl.outputs = {"y": "dst"}
         out = run_plan(pl, torch.zeros(1), extra={"src": x})["y"]
         np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=0, atol=1e-5)
+
+
+def test_load_reference_state_dict_with_key_map():
+    """Checkpoint hook (SURVEY 8b "state-dict names to accept"): Lightning-style keys with foreign inner names are
+    remapped by regex rules; training-only modules are dropped; a stray key still raises under strict."""
+    from centernet_lightning_b200.model import CenterNet
+    spec = spec_model.synth_init(spec_model.build_spec_model(3), seed=4)
+    foreign = {}
+    for k, v in spec.state_dict().items():
+        k = "model." + k
+        k = k.replace("model.backbone.conv1.", "model.backbone.stem.0.").replace("model.backbone.bn1.", "model.backbone.stem.1.")
+        k = k.replace(".block_1.conv.", ".block_1.0.").replace(".block_1.bn.", ".block_1.1.")
+        foreign[k] = v
+    foreign["model.backbone.fc.weight"] = torch.zeros(10, 512)
+    foreign["evaluator.count"] = torch.zeros(1)
+    net = CenterNet(3)
+    with pytest.raises(RuntimeError):
+        net.load_state_dict(foreign)
+    rules = {r"backbone\.stem\.0\.": "backbone.conv1.", r"backbone\.stem\.1\.": "backbone.bn1.",
+             r"\.block_1\.0\.": ".block_1.conv.", r"\.block_1\.1\.": ".block_1.bn."}
+    net.load_reference_state_dict(foreign, key_map=rules)
+    got = net.state_dict()
+    for k, v in spec.state_dict().items():
+        assert torch.equal(got["model." + k], v), k
+    foreign["model.neck.unknown.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        net.load_reference_state_dict(foreign, key_map=rules)
