@@ -38,7 +38,10 @@ def test_conv_probes_subset(cuda):
     names = {"1x1_64_64_w128_split", "3x3_256_256_w32_split", "3x3s2_64_128_w64_split", "1x1s2_64_128_w64_split",
              "3x3_64_64_res_split", "1x1_64_256_resup2_split", "1x1_256_80_nchw_split", "1x1_256_4_nchw_split",
              "3x3_group_off256_split", "3x3_512_512_w8_split", "3x3_64_64_w272_split", "3x3_64_64_w128_fast",
-             "3x3_512_256_up2_w16_split", "3x3_64_64_up2_w24x40_split", "deconv3_256_w16_split", "deconv4_128_w24x40_split"}
+             "3x3_512_256_up2_w16_split", "3x3_64_64_up2_w24x40_split", "deconv3_256_w16_split", "deconv4_128_w24x40_split",
+             "rows_3x3_64_64_w104x96_split", "rows_3x3_64_128_h8_w128_split", "rows_3x3_64_64_h8_w72_split",
+             "rows_3x3_64_64_w200_res_split", "rows_deconv4_64_w128_split", "rows_deconv3_64_w72_split",
+             "rows_3x3_64_64_up2_w128_split"}
     for c in conv_probe.PROBES:
         if c["name"] in names:
             ok, err = conv_probe.run(c, verbose=False)

@@ -49,6 +49,15 @@ PROBES = [
     cfg("deconv3_256_w16_split", 256, 256, 3, 1, 16, deconv=3),
     cfg("deconv4_64_w64_split", 64, 64, 4, 1, 64, deconv=4),
     cfg("deconv4_128_w24x40_split", 128, 128, 4, 1, (24, 40), n=1, deconv=4),
+    # row-rolling form (Cin = 64, rows wider than 64 pixels): ragged widths, short maps, batch crossing CTA runs,
+    # non-square phase windows and the upsampling store
+    cfg("rows_3x3_64_64_w104x96_split", 64, 64, 3, 1, (96, 104), n=3),
+    cfg("rows_3x3_64_128_h8_w128_split", 64, 128, 3, 1, (8, 128), n=5),
+    cfg("rows_3x3_64_64_h8_w72_split", 64, 64, 3, 1, (8, 72), n=2, relu=False),
+    cfg("rows_3x3_64_64_w200_res_split", 64, 64, 3, 1, (40, 200), n=2, res=1),
+    cfg("rows_deconv4_64_w128_split", 64, 64, 4, 1, (24, 128), n=2, deconv=4),
+    cfg("rows_deconv3_64_w72_split", 64, 64, 3, 1, (16, 72), n=1, deconv=3),
+    cfg("rows_3x3_64_64_up2_w128_split", 64, 64, 3, 1, (16, 128), n=2, up=1),
 ]
 
 
