@@ -33,7 +33,7 @@ from torch import nn
 from . import decode as _decode
 from . import _lib
 from .engine import Engine, PRECISION_FAST, PRECISION_SPLIT
-from .plan import RESNET_DEPTHS, RESNET_WIDTHS, build_plan
+from .plan import RESNET_DEPTHS, RESNET_WIDTHS, build_plan, resnet_out_channels
 
 _PRECISIONS = {"split": PRECISION_SPLIT, "fp32": PRECISION_SPLIT, "split_fused": 2, "fast": PRECISION_FAST, "fp16": PRECISION_FAST}
 
@@ -59,6 +59,20 @@ class _Block(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
 
 
+class _Bottleneck(nn.Module):
+    def __init__(self, cin, width, stride):
+        super().__init__()
+        cout = 4 * width
+        self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout)
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+
 class _Backbone(nn.Module):
     stride = 32
 
@@ -69,15 +83,18 @@ class _Backbone(nn.Module):
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
+        self.name = name
+        bottleneck = name == "resnet50"
         for i, (w, d) in enumerate(zip(RESNET_WIDTHS, RESNET_DEPTHS[name])):
             blocks = []
             for j in range(d):
-                blocks.append(_Block(cin, w, 2 if (j == 0 and i > 0) else 1))
-                cin = w
+                stride = 2 if (j == 0 and i > 0) else 1
+                blocks.append(_Bottleneck(cin, w, stride) if bottleneck else _Block(cin, w, stride))
+                cin = 4 * w if bottleneck else w
             setattr(self, f"layer{i + 1}", nn.Sequential(*blocks))
 
     def get_out_channels(self):
-        return list(RESNET_WIDTHS)
+        return list(resnet_out_channels(self.name))
 
 
 class _FPN(nn.Module):
@@ -366,7 +383,7 @@ class CenterNet(nn.Module):
                     mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
             elif isinstance(mod, nn.BatchNorm2d):
                 mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
-                if name.endswith("bn2"):
+                if name.endswith("bn3" if self.hparams.backbone == "resnet50" else "bn2") and ".layer" in name:
                     mod.weight.mul_(0.3)
                 mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
                 mod.running_mean.zero_()

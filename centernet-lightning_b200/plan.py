@@ -23,8 +23,13 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-RESNET_DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+RESNET_DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3)}
 RESNET_WIDTHS = (64, 128, 256, 512)
+
+
+def resnet_out_channels(backbone: str) -> Tuple[int, ...]:
+    """Channels of the four stage outputs: BasicBlock trunks keep the width, Bottleneck trunks (resnet50) expand x4."""
+    return tuple(w * (4 if backbone == "resnet50" else 1) for w in RESNET_WIDTHS)
 
 
 @dataclass
@@ -158,23 +163,38 @@ def build_plan(sd: Dict[str, torch.Tensor], *, backbone: str = "resnet34", neck:
     # ---- residual stages ----------------------------------------------------------------------
     feats: List[str] = []
     cin = 64
+    bottleneck = backbone == "resnet50"
+    out_ch = resnet_out_channels(backbone)
     for li, (width, depth) in enumerate(zip(RESNET_WIDTHS, RESNET_DEPTHS[backbone])):
         s_out = 4 * (2 ** li)
+        cout = out_ch[li]
         for bi in range(depth):
             stride = 2 if (bi == 0 and li > 0) else 1
             base = f"backbone.layer{li + 1}.{bi}"
             idt = cur
             if f"{base}.downsample.0.weight" in sd:
                 w, b = fold_bn(sd[f"{base}.downsample.0.weight"], _bn(sd, f"{base}.downsample.1"))
-                idt = p.add_buffer(f"{base}.idt", width, s_out)
-                p.ops.append(ConvOp(f"{base}.downsample", "conv", cur, idt, cin, width, 1, stride, 0, w, b, relu=False))
-            w, b = fold_bn(sd[f"{base}.conv1.weight"], _bn(sd, f"{base}.bn1"))
-            mid = p.add_buffer(f"{base}.mid", width, s_out)
-            p.ops.append(ConvOp(f"{base}.conv1", "conv", cur, mid, cin, width, 3, stride, 1, w, b, relu=True))
-            w, b = fold_bn(sd[f"{base}.conv2.weight"], _bn(sd, f"{base}.bn2"))
-            out = p.add_buffer(f"{base}.out", width, s_out)
-            p.ops.append(ConvOp(f"{base}.conv2", "conv", mid, out, width, width, 3, 1, 1, w, b, relu=True, residual=idt))
-            cur, cin = out, width
+                idt = p.add_buffer(f"{base}.idt", cout, s_out)
+                p.ops.append(ConvOp(f"{base}.downsample", "conv", cur, idt, cin, cout, 1, stride, 0, w, b, relu=False))
+            if bottleneck:
+                # torchvision v1.5 Bottleneck: 1x1 reduce -> 3x3 (carries the stride) -> 1x1 expand (+ identity) -> ReLU
+                w, b = fold_bn(sd[f"{base}.conv1.weight"], _bn(sd, f"{base}.bn1"))
+                m1 = p.add_buffer(f"{base}.mid1", width, s_out // stride)
+                p.ops.append(ConvOp(f"{base}.conv1", "conv", cur, m1, cin, width, 1, 1, 0, w, b, relu=True))
+                w, b = fold_bn(sd[f"{base}.conv2.weight"], _bn(sd, f"{base}.bn2"))
+                m2 = p.add_buffer(f"{base}.mid2", width, s_out)
+                p.ops.append(ConvOp(f"{base}.conv2", "conv", m1, m2, width, width, 3, stride, 1, w, b, relu=True))
+                w, b = fold_bn(sd[f"{base}.conv3.weight"], _bn(sd, f"{base}.bn3"))
+                out = p.add_buffer(f"{base}.out", cout, s_out)
+                p.ops.append(ConvOp(f"{base}.conv3", "conv", m2, out, width, cout, 1, 1, 0, w, b, relu=True, residual=idt))
+            else:
+                w, b = fold_bn(sd[f"{base}.conv1.weight"], _bn(sd, f"{base}.bn1"))
+                mid = p.add_buffer(f"{base}.mid", width, s_out)
+                p.ops.append(ConvOp(f"{base}.conv1", "conv", cur, mid, cin, width, 3, stride, 1, w, b, relu=True))
+                w, b = fold_bn(sd[f"{base}.conv2.weight"], _bn(sd, f"{base}.bn2"))
+                out = p.add_buffer(f"{base}.out", width, s_out)
+                p.ops.append(ConvOp(f"{base}.conv2", "conv", mid, out, width, width, 3, 1, 1, w, b, relu=True, residual=idt))
+            cur, cin = out, cout
         feats.append(cur)
 
     # ---- neck -----------------------------------------------------------------------------------
@@ -182,12 +202,12 @@ def build_plan(sd: Dict[str, torch.Tensor], *, backbone: str = "resnet34", neck:
         d = sd["neck.lateral.0.weight"].shape[0]
         w, b = fold_bn(sd["neck.lateral.3.weight"], None, sd["neck.lateral.3.bias"])
         x = p.add_buffer("neck.p5", d, 32)
-        p.ops.append(ConvOp("neck.lateral.3", "conv", feats[3], x, 512, d, 1, 1, 0, w, b, relu=False))
+        p.ops.append(ConvOp("neck.lateral.3", "conv", feats[3], x, out_ch[3], d, 1, 1, 0, w, b, relu=False))
         for i in (2, 1, 0):
             s = 4 * (2 ** i)
             w, b = fold_bn(sd[f"neck.lateral.{i}.weight"], None, sd[f"neck.lateral.{i}.bias"])
             fused = p.add_buffer(f"neck.sum{i}", d, s)
-            p.ops.append(ConvOp(f"neck.lateral.{i}", "conv", feats[i], fused, RESNET_WIDTHS[i], d, 1, 1, 0, w, b,
+            p.ops.append(ConvOp(f"neck.lateral.{i}", "conv", feats[i], fused, out_ch[i], d, 1, 1, 0, w, b,
                                 relu=False, residual=x, residual_up=2))
             w, b = fold_bn(sd[f"neck.output.{i}.conv.weight"], _bn(sd, f"neck.output.{i}.bn"))
             x = p.add_buffer(f"neck.out{i}", d, s)
@@ -197,7 +217,7 @@ def build_plan(sd: Dict[str, torch.Tensor], *, backbone: str = "resnet34", neck:
         # G1 "simple" neck (reference configs/base_resnet34.yaml:7-11, models/layers.py:71-99): on C5 only,
         # n x [conv3x3-BN-ReLU -> x2 upsample]; the upsample is nearest (fused into the conv's store: every output pixel
         # is written to its 2x2 block) or ConvTranspose2d(k, stride 2)-BN-ReLU (four sub-pixel phase convs).
-        x, cin_n, s = feats[3], 512, 32
+        x, cin_n, s = feats[3], out_ch[3], 32
         i = 0
         while f"neck.blocks.{i}.conv.weight" in sd:
             w, b = fold_bn(sd[f"neck.blocks.{i}.conv.weight"], _bn(sd, f"neck.blocks.{i}.bn"))

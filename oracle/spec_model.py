@@ -70,11 +70,37 @@ class BasicBlock(nn.Module):
         return F.relu(y + idt)
 
 
-_RESNET_DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+class Bottleneck(nn.Module):
+    """torchvision-compatible ResNet-50 Bottleneck (v1.5: the stride sits on the 3x3 conv), same parameter names."""
+    expansion = 4
+
+    def __init__(self, cin: int, width: int, stride: int):
+        super().__init__()
+        cout = width * self.expansion
+        self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = F.relu(self.bn2(self.conv2(y)))
+        y = self.bn3(self.conv3(y))
+        return F.relu(y + idt)
+
+
+_RESNET_DEPTHS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3)}
 
 
 class ResNetTrunk(nn.Module):
-    """ResNet-18/34 trunk without avgpool/fc.
+    """ResNet-18/34/50 trunk without avgpool/fc (resnet50 is one of the backbones the reference's
+    tests name, tests/test_models.py:37-39).
 
     Interface mirrors what models/meta.py:42,87-88,96 needs from a
     vision_toolbox backbone: forward_features, get_out_channels, stride.
@@ -90,16 +116,19 @@ class ResNetTrunk(nn.Module):
         self.bn1 = nn.BatchNorm2d(64)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         widths = (64, 128, 256, 512)
+        bottleneck = name == "resnet50"
+        self.out_channels = [w * (4 if bottleneck else 1) for w in widths]
         cin = 64
         for i, (w, d) in enumerate(zip(widths, depths)):
             blocks = []
             for j in range(d):
-                blocks.append(BasicBlock(cin, w, 2 if (j == 0 and i > 0) else 1))
-                cin = w
+                stride = 2 if (j == 0 and i > 0) else 1
+                blocks.append(Bottleneck(cin, w, stride) if bottleneck else BasicBlock(cin, w, stride))
+                cin = w * (4 if bottleneck else 1)
             setattr(self, f"layer{i + 1}", nn.Sequential(*blocks))
 
     def get_out_channels(self) -> List[int]:
-        return [64, 128, 256, 512]
+        return list(self.out_channels)
 
     def forward_features(self, x: torch.Tensor) -> List[torch.Tensor]:
         x = self.maxpool(F.relu(self.bn1(self.conv1(x))))
@@ -260,6 +289,8 @@ def synth_init(model: SpecModel, seed: int = 0, calib_size: int = 128, calib_bat
     for blk in model.modules():
         if isinstance(blk, BasicBlock):        # damp residual branches like a trained ResNet
             blk.bn2.weight.mul_(0.5)
+        elif isinstance(blk, Bottleneck):
+            blk.bn3.weight.mul_(0.5)
     for head in model.heads.children():
         head.out_conv.weight.mul_(out_gain / math.sqrt(2.0))
     # calibrate BN running stats with one train-mode pass (momentum=1 -> stats of this batch)

@@ -292,6 +292,26 @@ def test_inference_detection_equals_detect_on_oracle_preprocessed_images(cuda, t
         net.inference_detection(str(tmp_path / "missing"))
 
 
+def test_resnet50_bottleneck_trunk(cuda):
+    """resnet50 (reference tests/test_models.py:37-39): 1x1 / 3x3-stride / 1x1+residual Bottleneck launches with up to 2048
+    channels and FPN laterals on 256..2048 channels, against the CPU fp32 oracle."""
+    from centernet_lightning_b200.model import CenterNet
+    spec = spec_model.synth_init(spec_model.build_spec_model(12, backbone="resnet50"), seed=8)
+    net = CenterNet(12, backbone="resnet50", box_multiplier=16.0)
+    net.model.load_state_dict(spec.state_dict())
+    net = net.to(cuda)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand((2, 3, 160, 128), generator=g)
+    with torch.no_grad():
+        ref = spec(x)
+    out = net.model(x.to(cuda))
+    for k in ref:
+        assert tuple(out[k].shape) == tuple(ref[k].shape) == (2, ref[k].shape[1], 40, 32)
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=0, atol=TOL, err_msg=k)
+    det = net.detect(x.to(cuda))
+    assert tuple(det["boxes"].shape) == (2, 100, 4)
+
+
 def test_small_variant_resnet18_fpn128_heads128x2(cuda):
     """The other published variant (reference docs/experiments.md:24: FPN dim 128, heads w128 d2) on a ResNet-18 trunk
     (reference tests/test_models.py:37 lists resnet18): exercises Cout tiles of 128 and a 2-deep tower."""

@@ -122,3 +122,17 @@ def test_load_reference_state_dict_with_key_map():
     foreign["model.neck.unknown.weight"] = torch.zeros(1)
     with pytest.raises(RuntimeError):
         net.load_reference_state_dict(foreign, key_map=rules)
+
+
+def test_resnet50_bottleneck_plan_reproduces_oracle():
+    """resnet50 (reference tests/test_models.py:37-39 lists it): Bottleneck blocks lowered to 1x1 / 3x3(stride) / 1x1+residual
+    launches, FPN laterals on 256/512/1024/2048 channels; parameter count of the trunk = torchvision resnet50 minus fc."""
+    m = spec_model.synth_init(spec_model.build_spec_model(4, backbone="resnet50"), seed=7)
+    assert spec_model.count_params(m.backbone) == 23_508_032
+    pl = P.build_plan(m.state_dict(), backbone="resnet50")
+    x = cases.make_image(dict(n=1, size=64, img_seed=5))
+    with torch.no_grad():
+        ref = m(x)
+    out = run_plan(pl, x)
+    for k in ref:
+        np.testing.assert_allclose(out[k].numpy(), ref[k].numpy(), rtol=0, atol=2e-4)
