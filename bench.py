@@ -204,7 +204,7 @@ def run_ours(args):
         return last
     e2e_run(3)
     barrier()
-    e_steps = max(3, args.steps // 2)
+    e_steps = max(3, args.steps)        # the un-overlapped first H2D copy (pipeline fill) is inside the timed region
     ev0.record()
     e2e_run(e_steps)
     ev1.record()

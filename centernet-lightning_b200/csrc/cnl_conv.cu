@@ -546,48 +546,67 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 //   A plane-aware 3x3/2 max-pool finishes the stem.
 // ------------------------------------------------------------------------------------------------------------
 // T[n][sy][sx][dxi*12 + c*4 + py*2 + px] = image[n][c][2*sy + py][2*(sx + dxi - 2) + px]   (0 outside the image)
+// One thread builds the 64-channel row of one pixel; the rows of a warp's 32 consecutive pixels are contiguous in T
+// (4 KB per plane), so they are staged in shared memory and written back as eight fully coalesced 512-byte stores
+// (a thread storing its own 128-byte row touches 32 different lines per store instruction).
 template <int NPLANE>
 __global__ void __launch_bounds__(256)
 stem_im2row_kernel(const float* __restrict__ image, __half* __restrict__ T, int N, int H, int W, long long plane_elems) {
+  __shared__ uint4 s_rows[8][32][9];                 // [warp][pixel][8 chunks of 8 channels + 1 pad: conflict-free both ways]
   const int SH = H / 2, SW = W / 2;
+  const long long total = (long long)N * SH * SW;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)N * SH * SW) return;
-  const int sx = (int)(t % SW);
-  const int sy = (int)((t / SW) % SH);
-  const int n = (int)(t / ((long long)SW * SH));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pix0 = t - lane;                   // first pixel of this warp
   float v[64];
 #pragma unroll
-  for (int j = 48; j < 64; ++j) v[j] = 0.0f;
+  for (int j = 0; j < 64; ++j) v[j] = 0.0f;
+  if (t < total) {
+    const int sx = (int)(t % SW);
+    const int sy = (int)((t / SW) % SH);
+    const int n = (int)(t / ((long long)SW * SH));
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int py = 0; py < 2; ++py) {
-      const float* row = image + (((size_t)n * 3 + c) * H + (2 * sy + py)) * W;
+      for (int py = 0; py < 2; ++py) {
+        const float* row = image + (((size_t)n * 3 + c) * H + (2 * sy + py)) * W;
 #pragma unroll
-      for (int dxi = 0; dxi < 4; ++dxi) {
-        const int xs = sx + dxi - 2;
-        float2 f = make_float2(0.0f, 0.0f);
-        if (xs >= 0 && xs < SW) f = __ldg(reinterpret_cast<const float2*>(row + 2 * xs));
-        v[dxi * 12 + c * 4 + py * 2 + 0] = f.x;
-        v[dxi * 12 + c * 4 + py * 2 + 1] = f.y;
+        for (int dxi = 0; dxi < 4; ++dxi) {
+          const int xs = sx + dxi - 2;
+          float2 f = make_float2(0.0f, 0.0f);
+          if (xs >= 0 && xs < SW) f = __ldg(reinterpret_cast<const float2*>(row + 2 * xs));
+          v[dxi * 12 + c * 4 + py * 2 + 0] = f.x;
+          v[dxi * 12 + c * 4 + py * 2 + 1] = f.y;
+        }
       }
-    }
-  __half* o = T + (size_t)t * 64;
+  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 hi, lo;
-    __half2* hh = reinterpret_cast<__half2*>(&hi);
-    __half2* ll = reinterpret_cast<__half2*>(&lo);
+  for (int pl = 0; pl < NPLANE; ++pl) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float a = v[j * 8 + 2 * q], b = v[j * 8 + 2 * q + 1];
-      const __half2 h2 = __floats2half2_rn(a, b);
-      hh[q] = h2;
-      const float2 back = __half22float2(h2);
-      ll[q] = __floats2half2_rn(a - back.x, b - back.y);
+    for (int j = 0; j < 8; ++j) {
+      uint4 u;
+      __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = v[j * 8 + 2 * q], b = v[j * 8 + 2 * q + 1];
+        const __half2 h2 = __floats2half2_rn(a, b);
+        if (pl == 0) {
+          hh[q] = h2;
+        } else {
+          const float2 back = __half22float2(h2);
+          hh[q] = __floats2half2_rn(a - back.x, b - back.y);
+        }
+      }
+      s_rows[warp][lane][j] = u;
     }
-    reinterpret_cast<uint4*>(o)[j] = hi;
-    if (NPLANE == 2) reinterpret_cast<uint4*>(o + plane_elems)[j] = lo;
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(T + (size_t)pl * plane_elems + (size_t)pix0 * 64);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int q = it * 32 + lane;                  // 16-byte chunk index inside the warp's 4 KB block
+      if (pix0 + (q >> 3) < total) dst[q] = s_rows[warp][q >> 3][q & 7];
+    }
+    __syncwarp();
   }
 }
 
