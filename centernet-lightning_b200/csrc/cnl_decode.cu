@@ -478,6 +478,7 @@ constexpr int kListCap = 2048;
 constexpr int kBins = 2048;
 constexpr int kSubShift = kHistShift - 11;   // second-level digit: the next 11 key bits
 constexpr int kRefineAbove = 256;
+constexpr int kBoxPrefetchK = 256;           // box values of up to this many winners are prefetched during the label recovery
 constexpr int kLabelBatch = 3;               // classes per lane and batch in the label recovery (8 lanes x 3 = 24 classes at once)            // sort directly when bin_k-and-above holds at most this many
 
 // inclusive block scan over kSelThreads ints (warp shuffles + one smem hop)
@@ -506,15 +507,14 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int* s_warp /*[32]*/)
 }
 
 // reference centernet.py:278-303 for one detection: every fp32 op rounded separately (no FMA contraction)
-__device__ __forceinline__ float4 decode_box(const float* box_img, size_t plane, int idx, int H, int W,
-                                             int normalize, int box_log, float mult, float stride_f) {
-  const float* bx = box_img + idx;
+__device__ __forceinline__ float4 decode_box_from(const float (&g)[4], int idx, int H, int W,
+                                                  int normalize, int box_log, float mult, float stride_f) {
   float cx = __fadd_rn((float)(idx % W), 0.5f);
   float cy = __fadd_rn((float)(idx / W), 0.5f);
   float s[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    float gv = __ldg(bx + c * plane);
+    float gv = g[c];
     if (box_log) gv = expf(gv);
     gv = __fmul_rn(gv, mult);
     s[c] = fmaxf(gv, 0.0f);
@@ -529,6 +529,12 @@ __device__ __forceinline__ float4 decode_box(const float* box_img, size_t plane,
     x2 = __fmul_rn(x2, stride_f); y2 = __fmul_rn(y2, stride_f);
   }
   return make_float4(x1, y1, x2, y2);
+}
+__device__ __forceinline__ float4 decode_box(const float* box_img, size_t plane, int idx, int H, int W,
+                                             int normalize, int box_log, float mult, float stride_f) {
+  const float g[4] = {__ldg(box_img + idx), __ldg(box_img + plane + idx), __ldg(box_img + 2 * plane + idx),
+                      __ldg(box_img + 3 * plane + idx)};
+  return decode_box_from(g, idx, H, W, normalize, box_log, mult, stride_f);
 }
 
 // Stand-alone gather for caller-supplied indices (the reference's staticmethod is also used outside decode).
@@ -659,8 +665,9 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, uint
 // Out-of-place descending rank sort of n <= kSelThreads DISTINCT 64-bit keys (the flat index is part of the key):
 // rank(i) = #{j : keys[j] > keys[i]}.  1024/pow2(n) threads (at most 32) share one element; one barrier instead of the
 // ~log2(n)^2/2 barriers of the bitonic network, which dominated the select kernel for the usual n of 100..256.
-__device__ __forceinline__ void rank_sort_desc(const unsigned long long* keys, const uint32_t* pay, int n,
-                                               unsigned long long* out_keys, uint32_t* out_pay, int tid) {
+template <typename PAY>
+__device__ __forceinline__ void rank_sort_desc(const unsigned long long* keys, const PAY* pay, int n,
+                                               unsigned long long* out_keys, PAY* out_pay, int tid) {
   int np = 1;
   while (np < n) np <<= 1;
   int tpe = kSelThreads / np;                     // threads per element (power of two)
@@ -688,6 +695,11 @@ select_gather_kernel(DecodeParams p) {
   __shared__ int s_warp[32];
   __shared__ int s_scalars[3];
   __shared__ int s_n;
+  // class group of every collected candidate (CACHE path): carried through the sort so that the label recovery does not
+  // have to fetch it from global memory first (one dependent round trip less)
+  __shared__ uint8_t s_grp_in[kListCap];
+  __shared__ uint8_t s_grp_sorted[kSelThreads];
+  __shared__ float s_boxraw[4 * kBoxPrefetchK];       // raw box-map values of the winners, fetched together with their class values
 
   const int n = blockIdx.x;
   const int tid = threadIdx.x;
@@ -702,11 +714,14 @@ select_gather_kernel(DecodeParams p) {
   const int n_vec = vec4 ? (HW >> 2) : 0;
 
   float4 cache[4];
+  uint32_t cgrp[4];
   if (CACHE) {
+    const uint32_t* cg32 = reinterpret_cast<const uint32_t*>(p.cgroup + (size_t)n * HW);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = tid + q * kSelThreads;
       cache[q] = (i < n_vec) ? sc4[i] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);   // -inf sorts below every candidate
+      cgrp[q] = (i < n_vec) ? cg32[i] : 0u;
     }
   }
   // visit(f): f(key, flat_index, valid) for every candidate of this thread, called the SAME number of times by every
@@ -718,7 +733,7 @@ select_gather_kernel(DecodeParams p) {
         const int i = tid + q * kSelThreads;
         const float fv[4] = {cache[q].x, cache[q].y, cache[q].z, cache[q].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec);
+        for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec, (cgrp[q] >> (8 * j)) & 0xffu);
       }
     } else {
       // larger maps: 4 independent 16-byte loads per thread and round trip (the candidate map is L2-resident; one load
@@ -735,25 +750,29 @@ select_gather_kernel(DecodeParams p) {
           const int i = i0 + q * kSelThreads + tid;
           const float fv[4] = {v4[q].x, v4[q].y, v4[q].z, v4[q].w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec);
+          for (int j = 0; j < 4; ++j) f(sortable_key(fv[j]), 4 * i + j, i < n_vec, 0xffu);
         }
       }
       for (int i0 = 4 * n_vec; i0 < HW; i0 += kSelThreads) {
         const int i = i0 + tid;
         const bool ok = i < HW;
-        f(sortable_key(ok ? sc[i] : 0.f), i, ok);
+        f(sortable_key(ok ? sc[i] : 0.f), i, ok, 0xffu);
       }
     }
   };
   // warp-aggregated append to s_list: one shared-memory atomic per warp and step instead of one per element
-  auto append = [&](bool pred, unsigned long long entry) {
+  auto append = [&](bool pred, unsigned long long entry, uint32_t grp) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
     if (m == 0) return;
     const int lane = tid & 31, leader = __ffs(m) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(&s_n, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) s_list[base + __popc(m & ((1u << lane) - 1u))] = entry;
+    if (pred) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      s_list[pos] = entry;
+      if (CACHE) s_grp_in[pos] = (uint8_t)grp;
+    }
   };
 
   // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
@@ -790,7 +809,7 @@ select_gather_kernel(DecodeParams p) {
   bool done = false;
   if (n_in_or_above <= kRefineAbove) {
     // few enough: collect every candidate in bin_k or above and sort them all
-    visit([&](uint32_t u, int i, bool ok) { append(ok && (u >> kHistShift) >= bin_k, pack_entry(u, i)); });
+    visit([&](uint32_t u, int i, bool ok, uint32_t g) { append(ok && (u >> kHistShift) >= bin_k, pack_entry(u, i), g); });
     n_sort = n_in_or_above;
     done = true;
   } else {
@@ -799,9 +818,9 @@ select_gather_kernel(DecodeParams p) {
     // of bin_k at or above the sub-bin that holds the k-th largest.
     for (int i = tid; i < kBins; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
-    visit([&](uint32_t u, int i, bool ok) {
+    visit([&](uint32_t u, int i, bool ok, uint32_t g) {
       const uint32_t b = u >> kHistShift;
-      append(ok && b > bin_k, pack_entry(u, i));
+      append(ok && b > bin_k, pack_entry(u, i), g);
       if (ok && b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
     });
     __syncthreads();
@@ -819,8 +838,8 @@ select_gather_kernel(DecodeParams p) {
     const uint32_t sub_k = (uint32_t)s_scalars[0];
     const int n_total = n_above + s_scalars[1];
     if (n_total <= kListCap) {
-      visit([&](uint32_t u, int i, bool ok) {
-        append(ok && (u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k, pack_entry(u, i));
+      visit([&](uint32_t u, int i, bool ok, uint32_t g) {
+        append(ok && (u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k, pack_entry(u, i), g);
       });
       n_sort = n_total;
       done = true;
@@ -834,8 +853,10 @@ select_gather_kernel(DecodeParams p) {
   // ---- sort, descending -------------------------------------------------------------------------------------
   const unsigned long long* s_sorted = s_list;
   __syncthreads();
+  bool have_grp = false;                             // s_grp_sorted[j] = class group of winner j
   if (n_sort <= kSelThreads) {                       // the usual case: k .. a few hundred collected candidates
-    rank_sort_desc(s_list, nullptr, n_sort, s_list + kSelThreads, nullptr, tid);
+    have_grp = CACHE && done;
+    rank_sort_desc<uint8_t>(s_list, have_grp ? s_grp_in : nullptr, n_sort, s_list + kSelThreads, s_grp_sorted, tid);
     s_sorted = s_list + kSelThreads;
   } else {
     int kp = 1;
@@ -855,6 +876,7 @@ select_gather_kernel(DecodeParams p) {
   const size_t plane = (size_t)HW;
   const float* img = p.heat + (size_t)n * p.C * plane;
   const int sub = tid & 7;
+  const bool box_pre = (p.box != nullptr) && (k <= kBoxPrefetchK);
   const int scan_len = (p.group_classes > 0) ? p.group_classes : p.C;       // classes to re-read per winner (CTA-uniform)
   for (int j0 = 0; j0 < k; j0 += kSelThreads / 8) {
     const int j = j0 + (tid >> 3);
@@ -872,9 +894,12 @@ select_gather_kernel(DecodeParams p) {
     // pixel are 4*H*W bytes apart - same DRAM bank - so every class read costs a row activation)
     int c_lo = 0, c_hi = p.C;
     if (act) {
-      const int gid = p.cgroup[(size_t)n * HW + idx];
+      const int gid = have_grp ? (int)s_grp_sorted[j] : (int)p.cgroup[(size_t)n * HW + idx];
       if (gid != 0xff) { c_lo = gid * p.group_classes; c_hi = min(p.C, c_lo + p.group_classes); }
     }
+    // the winners' box-map values travel with their class values (independent loads, same round trip)
+    float braw = 0.f;
+    if (box_pre && act && sub < 4) braw = __ldg(p.box + ((size_t)n * 4 + sub) * plane + idx);
     const bool multi_batch = scan_len > 8 * kLabelBatch;
     for (int off = 0; off < scan_len; off += 8 * kLabelBatch) {              // uniform trip count for the whole CTA
       float xv[kLabelBatch];
@@ -914,11 +939,12 @@ select_gather_kernel(DecodeParams p) {
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (box_pre && act && sub < 4) s_boxraw[4 * j + sub] = braw;
     if (act && sub == 0) {
       float score = p.from_logits ? sigmoid32(v) : v;
       uint32_t label = (first == 0x7fffffff) ? 0u : (uint32_t)first;
       if (score == 0.0f) label = 0u;                       // underflowed / zero candidates arg-max to class 0
-      s_label[j] = label;
+      s_label[j] = label | ((uint32_t)j << 16);            // class (< 65536) + position before the re-sort (< 1024)
       // canonical output order is (score desc, index asc): distinct logits can round to one probability, so re-key
       // (into a second list: the first one is still being read by the other lanes of this winner)
       s_out[j] = pack_entry(sortable_key(score), idx);
@@ -929,7 +955,7 @@ select_gather_kernel(DecodeParams p) {
   const uint32_t* s_fin_label = s_label;
   if (p.from_logits) {                               // s_list is free again: sorted keys in its first half, labels behind
     uint32_t* lab2 = reinterpret_cast<uint32_t*>(s_list + kSelThreads);
-    rank_sort_desc(s_out, s_label, k, s_list, lab2, tid);
+    rank_sort_desc<uint32_t>(s_out, s_label, k, s_list, lab2, tid);
     s_fin = s_list;
     s_fin_label = lab2;
   }
@@ -941,9 +967,17 @@ select_gather_kernel(DecodeParams p) {
     size_t o = (size_t)n * k + j;
     p.scores[o] = key_to_float((uint32_t)(w >> 32));
     p.indices[o] = idx;
-    p.labels[o] = (long long)s_fin_label[j];
+    const uint32_t lab = s_fin_label[j];
+    p.labels[o] = (long long)(lab & 0xffffu);
     if (p.box == nullptr) continue;
-    float4 b4 = decode_box(p.box + (size_t)n * 4 * plane, plane, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
+    float4 b4;
+    if (box_pre) {
+      const int oj = (int)(lab >> 16);
+      const float g[4] = {s_boxraw[4 * oj], s_boxraw[4 * oj + 1], s_boxraw[4 * oj + 2], s_boxraw[4 * oj + 3]};
+      b4 = decode_box_from(g, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
+    } else {
+      b4 = decode_box(p.box + (size_t)n * 4 * plane, plane, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
+    }
     *reinterpret_cast<float4*>(p.boxes + o * 4) = b4;
   }
   if (p.reid != nullptr) {                    // fairmot.py:63-73: emb[n, j, e] = reid[n, e, idx_j]

@@ -363,6 +363,27 @@ class CenterNet(nn.Module):
             host["embeddings"] = det["embeddings"].cpu().numpy()
         return [{k: v[i] for k, v in host.items()} for i in range(images.shape[0])]
 
+    # ---- validation tail (reference models/centernet.py:202-218) ------------------------------------------------
+    evaluator = None          # any object with update(preds, targets) / get_metrics() / reset(), e.g. the reference's CocoEvaluator
+
+    def validation_step(self, batch, batch_idx: int = 0):
+        """``images, targets = batch``: forward + decode + xyxy->xywh on the GPU (predict_step), per-image numpy dicts,
+        targets filtered to ``boxes`` / ``labels`` and handed to ``self.evaluator.update`` exactly as the reference does.
+        The COCO evaluator itself (pycocotools) is the caller's: assign it to ``self.evaluator``."""
+        import numpy as np
+        images, targets = batch
+        preds = self.predict_step(images.to(next(self.parameters()).device))
+        targets = [{k: np.array(t[k]) for k in ("boxes", "labels")} for t in targets]
+        if self.evaluator is None:
+            raise RuntimeError("validation_step needs an evaluator: set model.evaluator (update / get_metrics / reset)")
+        self.evaluator.update(preds, targets)
+        return preds
+
+    def validation_epoch_end(self, outputs=None) -> Dict[str, float]:
+        metrics = self.evaluator.get_metrics()
+        self.evaluator.reset()
+        return {f"val/{k}": v for k, v in metrics.items()}
+
     def invalidate(self) -> None:
         self._graphs.clear()
         self.model.invalidate()

@@ -292,6 +292,38 @@ def test_inference_detection_equals_detect_on_oracle_preprocessed_images(cuda, t
         net.inference_detection(str(tmp_path / "missing"))
 
 
+def test_validation_step_feeds_an_evaluator(cuda):
+    """reference models/centernet.py:202-218: per-image dicts with xywh boxes + filtered targets reach evaluator.update."""
+    from centernet_lightning_b200.model import CenterNet
+
+    class Recorder:
+        def __init__(self):
+            self.seen = []
+        def update(self, preds, targets):
+            self.seen.append((preds, targets))
+        def get_metrics(self):
+            return {"n": float(sum(len(p) for p, _ in self.seen))}
+        def reset(self):
+            self.seen = []
+
+    net = CenterNet(5, box_multiplier=16.0, num_detections=10).init_synthetic_(4).to(cuda)
+    net.evaluator = Recorder()
+    x = torch.rand((2, 3, 64, 64))
+    targets = [{"boxes": [[1, 2, 3, 4]], "labels": [1], "image_id": 7}, {"boxes": [], "labels": [], "image_id": 8}]
+    preds = net.validation_step((x, targets), 0)
+    det = net.detect(x.to(cuda))
+    assert len(preds) == 2 and set(preds[0]) == {"boxes", "scores", "labels"}
+    xyxy = det["boxes"].cpu().numpy()
+    np.testing.assert_array_equal(preds[1]["boxes"][:, :2], xyxy[1][:, :2])
+    np.testing.assert_array_equal(preds[1]["boxes"][:, 2:], xyxy[1][:, 2:] - xyxy[1][:, :2])
+    (p, t), = net.evaluator.seen
+    assert set(t[0]) == {"boxes", "labels"} and t[0]["boxes"].shape == (1, 4)
+    assert net.validation_epoch_end() == {"val/n": 2.0} and net.evaluator.seen == []
+    net.evaluator = None
+    with pytest.raises(RuntimeError):
+        net.validation_step((x, targets), 0)
+
+
 def test_resnet50_bottleneck_trunk(cuda):
     """resnet50 (reference tests/test_models.py:37-39): 1x1 / 3x3-stride / 1x1+residual Bottleneck launches with up to 2048
     channels and FPN laterals on 256..2048 channels, against the CPU fp32 oracle."""
