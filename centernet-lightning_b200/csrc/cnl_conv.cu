@@ -95,7 +95,16 @@ struct ConvParams {
 // tap (r, s) is a shifted view of a slot: start address = slot of input row (h + r - pad_h) + s pixels x 128 B - the
 // 128-byte swizzle is a function of the shared-memory address bits, so a view that starts s rows into a swizzle atom reads
 // exactly what TMA wrote there.  Only the weight tiles still stream through the stage ring.
-template <int NPLANE, bool CORR, bool ROWS>
+//
+// PAIR = true (Cout tile 256, split precision): the two CTAs of a cluster form a tcgen05 CTA pair (cta_group::2).  Each
+// CTA loads its own 128-pixel A tile and HALF of the weight tile (128 of the 256 Cout rows); the leader CTA issues
+// M = 256 instructions that read A and B from both CTAs' shared memory and write each CTA's 128 accumulator rows into
+// its own TMEM.  Per k-step a CTA then takes in 64 KB instead of 96 KB - the im2col kernel with full weight tiles sits
+// at ~52 B/clk of shared-memory fill per SM, which is what capped its tensor pipe at ~83 % - and three stages fit
+// instead of two.  Barrier protocol: both CTAs' TMA loads credit the LEADER's full barrier; the leader's
+// tcgen05.commit multicasts to both CTAs' empty / accumulator-full barriers; the peer's epilogue warps arrive remotely on
+// the leader's accumulator-empty barrier.
+template <int NPLANE, bool CORR, bool ROWS, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap w_map,
                const __grid_constant__ CUtensorMap dst_map, const ConvParams p) {
@@ -113,7 +122,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
   const int b_tile_bytes = p.n_tile * kBlockK * 2;
-  const int stage_bytes = ROWS ? NPLANE * b_tile_bytes : NPLANE * (kATileBytes + b_tile_bytes);   // ROWS: stages hold weights only
+  const int b_half_bytes = b_tile_bytes / 2;                            // PAIR: this CTA's half of the weight tile
+  const int stage_bytes = ROWS ? NPLANE * b_tile_bytes                  // ROWS: stages hold weights only
+                        : PAIR ? NPLANE * (kATileBytes + b_half_bytes)
+                               : NPLANE * (kATileBytes + b_tile_bytes);
   const int a_ring_bytes = ROWS ? p.a_slots * NPLANE * p.a_slot_bytes : 0;
   uint8_t* a_ring = smem;                                               // ROWS: [a_slots][NPLANE][a_slot_bytes]
   uint8_t* stages = smem + a_ring_bytes;
@@ -125,14 +137,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     ptx::prefetch_tmap(&src_map);
     ptx::prefetch_tmap(&w_map);
     if (p.out_mode == 0) ptx::prefetch_tmap(&dst_map);
-    for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], p.cluster); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], kEpiWarps); }
+    for (int i = 0; i < p.num_stages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], PAIR ? 1 : p.cluster); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full_bar[i], 1); ptx::mbar_init(&tmem_empty_bar[i], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     if (ROWS) for (int i = 0; i < p.a_slots; ++i) { ptx::mbar_init(&a_full_bar[i], 1); ptx::mbar_init(&a_empty_bar[i], 1); }
     ptx::fence_barrier_init();
   }
+  if (PAIR) ptx::cluster_sync_all();                // both CTAs are resident before the pair allocates tensor memory
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_base_smem, 512);
-    ptx::tmem_relinquish();
+    if (PAIR) { ptx::tmem_alloc_pair(&tmem_base_smem, 512); ptx::tmem_relinquish_pair(); }
+    else      { ptx::tmem_alloc(&tmem_base_smem, 512); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -194,7 +207,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
       }
     }
-    if (!ROWS && lane == 0) {
+    if (PAIR && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int b_rows = p.n_tile / 2;
+      for (int grp = group0; grp < total_groups; grp += group_step) {
+        const int n_idx = grp % p.n_tiles;
+        int m_idx = (grp / p.n_tiles) * 2 + crank;
+        int img = m_idx / tiles_per_img;
+        m_idx -= img * tiles_per_img;
+        if (img >= p.n_img) img = 1 << 20;                // dummy tile: every coordinate out of bounds
+        const int h0 = (m_idx / p.tiles_w) * p.th;
+        const int w0 = (m_idx % p.tiles_w) * p.tw;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.kw, sx = tap - r * p.kw;
+          const int cw = w0 * p.stride + sx - p.pad_w;
+          const int ch = h0 * p.stride + r - p.pad_h;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            // the leader's barrier collects the bytes of BOTH CTAs' loads for this stage
+            if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+            const uint32_t bar = ptx::mapa_u32(&full_bar[stage], 0);
+            uint8_t* st = stages + (size_t)stage * stage_bytes;
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl)
+              ptx::tma_load_4d_pair(st + pl * kATileBytes, &src_map, bar, p.src_c_off + kb * kBlockK, cw, ch, img + pl * p.n_img);
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl)
+              ptx::tma_load_3d_pair(st + NPLANE * kATileBytes + pl * b_half_bytes, &w_map, bar, kb * kBlockK,
+                                    n_idx * p.n_tile + crank * b_rows, tap + pl * taps);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    if (!ROWS && !PAIR && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.n_tile / csize;
@@ -282,7 +329,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         ptx::umma_commit(&tmem_full_bar[as]);
       }
     }
-    if (!ROWS && lane == 0) {
+    if (PAIR && lane == 0 && crank == 0) {
+      // leader of the CTA pair: M = 256 (128 accumulator rows in each CTA's tensor memory), N = n_tile
+      const uint32_t idesc = ptx::make_idesc_f16_m256((uint32_t)p.n_tile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_it = 0;
+      for (int grp = group0; grp < total_groups; grp += group_step, ++acc_it) {
+        const int as = two_acc ? (acc_it & 1) : 0;
+        const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);       // the epilogue warps of BOTH CTAs have drained their halves
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        const uint32_t d_corr = CORR ? (d_tmem + p.corr_off) : d_tmem;
+        for (int it = 0; it < k_iters; ++it) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(stages + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + NPLANE * kATileBytes;
+          const uint64_t a_hi = ptx::make_sw128_kmajor_desc(a_addr);
+          const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + kATileBytes);
+          const uint64_t b_hi = ptx::make_sw128_kmajor_desc(b_addr);
+          const uint64_t b_lo = ptx::make_sw128_kmajor_desc(b_addr + b_half_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);
+            ptx::umma_f16_pair(d_tmem, a_hi + koff, b_hi + koff, idesc, (it | k) != 0);
+            if (NPLANE == 2) {
+              ptx::umma_f16_pair(d_corr, a_hi + koff, b_lo + koff, idesc, CORR ? (uint32_t)((it | k) != 0) : 1u);
+              ptx::umma_f16_pair(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
+            }
+          }
+          ptx::umma_commit_pair(&empty_bar[stage], 0b11);       // the stage is reusable in both CTAs
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_pair(&tmem_full_bar[as], 0b11);        // both CTAs' epilogues may read their accumulator rows
+      }
+    }
+    if (!ROWS && !PAIR && lane == 0) {
       const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
       // cat: the hi and lo weight tiles sit back to back in the stage (n_tile rows of 128 B each, whole swizzle atoms),
       // so A_hi x [B_hi | B_lo] is ONE instruction of N = 2*n_tile whose columns [n_tile, 2*n_tile) are the correction
@@ -522,7 +606,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       // accumulator drained: hand the TMEM stage back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(&tmem_empty_bar[as], 0));   // the leader issues the MMAs
+        else                    ptx::mbar_arrive(&tmem_empty_bar[as]);
+      }
     }
     if (lane == 0) ptx::tma_store_wait_all<0>();
   }
@@ -532,7 +619,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
   if (p.cluster > 1) ptx::cluster_sync_all();       // no peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, 512);
+    else      ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -714,6 +802,7 @@ struct OpInfo {
   int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off, cat;
   int kh, kw, pad_h, pad_w, up;         // resolved kernel extent / padding, destination scale (1 or 2)
   int rows, a_slots, a_slot_bytes, box_w; // ROWS mode geometry (rows = 0: im2col tiles)
+  int pair;                               // CTA-pair (cta_group::2) form
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
@@ -861,6 +950,16 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   op.corr_off = op.cat ? op.n_tile : ((op.n_tile <= 128) ? 128 : 256);
   op.acc_stages = (split_corr && op.n_tile > 128) ? 1 : 2;
   plan_rows_mode(op, planes, d.cin, d.stride, !dst.fp32_nchw, e->precision);
+  // CTA pair (cta_group::2): Cout tiles of 256 in split precision with the separate correction accumulator
+  static const bool pair_on = [] { const char* v = getenv("CNL_PAIR"); return !(v && atoi(v) == 0); }();
+  op.pair = 0;
+  if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && op.n_tile == 256 && !op.rows && !dst.fp32_nchw &&
+      op.cluster == 1 && e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= 1024) {     // short launches (layer3/4) measure 5-7 % slower as pairs
+    op.pair = 1;
+    op.cluster = 2;                                  // launch as clusters of 2; each CTA's weight box is n_tile / 2 rows
+    const int pair_stage = planes * (kATileBytes + op.n_tile / 2 * kBlockK * 2);
+    op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / pair_stage);
+  }
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = op.kh * op.kw;
@@ -936,6 +1035,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   op.cat = (e->precision == CNL_PRECISION_SPLIT) && cat_enabled();
   op.corr = op.cat;                        // K = 256: the correction accumulator only comes with the cat MMA
   op.corr_off = op.cat ? 64 : 128; op.acc_stages = 2;
+  op.pair = 0;
   plan_rows_mode(op, planes, 64, 1, true, e->precision);
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
@@ -1034,10 +1134,11 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
   CNL_CUDA_CHECK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, e->device));
   if (cc_major != 10) return fail(CNL_ERR_UNSUPPORTED, "cnl_b200 kernels are built for sm_100a only (device has compute capability %d.x)", cc_major);
   e->num_sms = dev_sms;
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CNL_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<2, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   uint8_t* base = static_cast<uint8_t*>(arena);
   const int planes = e->planes;
   for (OpInfo& op : e->ops) {
@@ -1135,12 +1236,13 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     cfg.numAttrs = pdl ? 2 : 1;
     if (op.rows) {
       cfg.gridDim = dim3(std::min(p.m_tiles, e->num_sms));
-      return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, true>, op.src_map, op.w_map, op.dst_map, p);
+      return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, true, false>, op.src_map, op.w_map, op.dst_map, p);
     }
-    if (e->precision == CNL_PRECISION_SPLIT && op.corr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, false>, op.src_map, op.w_map, op.dst_map, p);
-    else if (e->precision == CNL_PRECISION_SPLIT)       return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, op.src_map, op.w_map, op.dst_map, p);
-    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false>, op.src_map, op.w_map, op.dst_map, p);
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false>, op.src_map, op.w_map, op.dst_map, p);
+    if (op.pair) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, false, true>, op.src_map, op.w_map, op.dst_map, p);
+    if (e->precision == CNL_PRECISION_SPLIT && op.corr) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, true, false, false>, op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT)       return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false, false>, op.src_map, op.w_map, op.dst_map, p);
+    else if (e->precision == CNL_PRECISION_SPLIT_FUSED) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, false, false, false>, op.src_map, op.w_map, op.dst_map, p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, false, false>, op.src_map, op.w_map, op.dst_map, p);
   };
   for (int i = first_op; i < last_op; ++i) {
     OpInfo& op = e->ops[i];
