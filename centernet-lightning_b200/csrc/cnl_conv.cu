@@ -73,6 +73,7 @@ struct ConvParams {
   int a_slots;                  // row slots in the ring (>= kh + 1)
   int a_slot_bytes;             // bytes of one slot and plane: (tw + kw - 1) pixels x 128 B, rounded up to 1024
   int box_w;                    // pixels per loaded row: tw + kw - 1
+  int stage_depth;              // epilogue staging buffers per warp (ring): TMA stores of the last depth-1 chunks may still be in flight
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -420,7 +421,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                    // which half of the tile's columns this warp drains
     const int lane_base = q * 32;
-    uint8_t* my_stage = staging + (size_t)(warp - 2) * NPLANE * kStageWarpBytes;
+    uint8_t* const my_stage_base = staging + (size_t)(warp - 2) * p.stage_depth * NPLANE * kStageWarpBytes;
+    int sbuf = 0;                                       // ring position inside this warp's staging buffers
     int acc_it = 0;
     const int it_begin = ROWS ? rows_t0 : group0, it_end = ROWS ? rows_t1 : total_groups, it_step = ROWS ? 1 : group_step;
     for (int grp = it_begin; grp < it_end; grp += it_step, ++acc_it) {
@@ -517,8 +519,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
-          // the previous TMA store out of this warp's staging buffers must have finished reading them
-          if (lane == 0) ptx::tma_store_wait_read<0>();
+          // The TMA unit serves this warp's small stores behind the producer's 64-96 KB loads, so a store takes ~1 us to
+          // finish reading its staging buffer; with ONE buffer per warp every chunk waited for the previous chunk's store
+          // (80 % of the epilogue's busy samples, and the epilogue is exposed whenever the accumulator is not double
+          // buffered).  With a ring of `stage_depth` buffers only the store issued depth chunks ago has to be done.
+          uint8_t* my_stage = my_stage_base + (size_t)sbuf * NPLANE * kStageWarpBytes;
+          if (++sbuf == p.stage_depth) sbuf = 0;
+          if (lane == 0) {
+            if (p.stage_depth >= 3)      ptx::tma_store_wait_read<2>();
+            else if (p.stage_depth == 2) ptx::tma_store_wait_read<1>();
+            else                         ptx::tma_store_wait_read<0>();
+          }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                  // 8 channels = one 16-byte chunk; rows are 64 B, SWIZZLE_64B
@@ -803,6 +814,7 @@ struct OpInfo {
   int kh, kw, pad_h, pad_w, up;         // resolved kernel extent / padding, destination scale (1 or 2)
   int rows, a_slots, a_slot_bytes, box_w; // ROWS mode geometry (rows = 0: im2col tiles)
   int pair;                               // CTA-pair (cta_group::2) form
+  int stage_depth;                        // epilogue staging ring depth (1..3)
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
   float wscale;
   size_t w_offset, bias_offset, scratch_offset;
@@ -953,12 +965,19 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   // CTA pair (cta_group::2): Cout tiles of 256 in split precision with the separate correction accumulator
   static const bool pair_on = [] { const char* v = getenv("CNL_PAIR"); return !(v && atoi(v) == 0); }();
   op.pair = 0;
+  op.stage_depth = 1;
   if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && op.n_tile == 256 && !op.rows && !dst.fp32_nchw &&
       op.cluster == 1 && e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= 1024) {     // short launches (layer3/4) measure 5-7 % slower as pairs
     op.pair = 1;
     op.cluster = 2;                                  // launch as clusters of 2; each CTA's weight box is n_tile / 2 rows
     const int pair_stage = planes * (kATileBytes + op.n_tile / 2 * kBlockK * 2);
-    op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / pair_stage);
+    // the pair's smaller stages leave room for three load stages + one staging buffer per warp (default) or two stages + a
+    // 2-/3-deep staging ring (CNL_STAGE_DEPTH; measured equal: at the board's power cap removing idle time from the
+    // epilogue only lowers the clock)
+    static const int env_depth = [] { const char* v = getenv("CNL_STAGE_DEPTH"); return v ? atoi(v) : 1; }();
+    op.stage_depth = std::max(1, std::min(3, env_depth));
+    op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - op.stage_depth * staging) / pair_stage);
+    if (op.num_stages < 2) { op.stage_depth = 1; op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / pair_stage); }
   }
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
@@ -1036,6 +1055,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   op.corr = op.cat;                        // K = 256: the correction accumulator only comes with the cat MMA
   op.corr_off = op.cat ? 64 : 128; op.acc_stages = 2;
   op.pair = 0;
+  op.stage_depth = 1;
   plan_rows_mode(op, planes, 64, 1, true, e->precision);
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
@@ -1260,7 +1280,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
     p.acc_stages = op.acc_stages; p.corr_off = op.corr_off; p.cat = op.cat;
     p.dst_up = 1; p.dst_phase = -1; p.dst_c = dst.channels;
-    p.a_slots = op.a_slots; p.a_slot_bytes = op.a_slot_bytes; p.box_w = op.box_w;
+    p.a_slots = op.a_slots; p.a_slot_bytes = op.a_slot_bytes; p.box_w = op.box_w; p.stage_depth = op.stage_depth;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
