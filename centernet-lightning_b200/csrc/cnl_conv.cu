@@ -966,10 +966,16 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   static const bool pair_on = [] { const char* v = getenv("CNL_PAIR"); return !(v && atoi(v) == 0); }();
   op.pair = 0;
   op.stage_depth = 1;
-  if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && op.n_tile == 256 && !op.rows && !dst.fp32_nchw &&
+  // Cout tiles of 128 as pairs (CNL_PAIR128=1) measure 4 % SLOWER than the single-CTA [hi|lo] form: there the A operand's
+  // shared-memory read (streamed twice instead of three times) matters more than the fill traffic
+  static const bool pair128 = [] { const char* v = getenv("CNL_PAIR128"); return v && atoi(v) != 0; }();
+  if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && (op.n_tile == 256 || (op.n_tile == 128 && pair128)) && !op.rows && !dst.fp32_nchw &&
       op.cluster == 1 && e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= 1024) {     // short launches (layer3/4) measure 5-7 % slower as pairs
     op.pair = 1;
     op.cluster = 2;                                  // launch as clusters of 2; each CTA's weight box is n_tile / 2 rows
+    if (op.n_tile == 128) {                          // the pair splits the weight rows, so the [hi|lo] concatenation is not used:
+      op.cat = 0; op.corr_off = 128; op.acc_stages = 2;   // three N = 128 instructions, accumulators at columns 0 / 128, two stages
+    }
     const int pair_stage = planes * (kATileBytes + op.n_tile / 2 * kBlockK * 2);
     // the pair's smaller stages leave room for three load stages + one staging buffer per warp (default) or two stages + a
     // 2-/3-deep staging ring (CNL_STAGE_DEPTH; measured equal: at the board's power cap removing idle time from the
