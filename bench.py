@@ -235,10 +235,10 @@ def run_ours(args):
         burst, sustained, hbm, src = _peaks()
         flops = 2.0 * TOWER_GMAC * 1e9 * BATCH_PER_GPU
         achieved = flops / (k_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (3x3 256->256 @128x128, op heads.heatmap.block_2)",
+        roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<2,true,false,true> (CTA-pair tcgen05 implicit GEMM; 3x3 256->256 @128x128, op heads.heatmap.block_2)",
                     "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                     "peak_source": f"{src} bf16 burst (kernel timed alone, {reps} launches)", "kernel_ms": k_ms,
-                    "algorithmic_flops_per_launch": flops, "traffic": 1049.6e6, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (547.3 + 502.3 MB; algorithmic 2 x 536.9 MB), profiles/r01_tower_conv_ncu_details.txt",
+                    "algorithmic_flops_per_launch": flops, "traffic": 1044.0e6, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (545.1 + 499.0 MB; algorithmic 2 x 536.9 MB), profiles/r01_tower_conv_ncu_details.txt",
                     "tensor_passes": 1 if args.precision == "fast" else 3}
         # ---- decode kernel: HBM roofline (second headline of BASELINE.json) ------------------------------------
         from centernet_lightning_b200 import decode as cdec
@@ -276,8 +276,8 @@ def run_ours(args):
         decode_roof = {"bound": "hbm", "kernel": "whole decode: peaks_fast_kernel + select_gather_kernel (CUDA-graph replay, network's own heatmap)",
                        "achieved": d_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                        "frac": d_bytes / (d_ms * 1e-3) / 1e9 / hbm, "decode_us": d_ms * 1e3,
-                       "peaks_kernel_only": {"us": 32.96, "achieved": 5091.0, "frac": round(5091.0 / hbm, 3), "traffic": 172.6e6,
-                                             "source": "ncu --set full of peaks_fast_kernel (gpu__time_duration, dram__bytes_read 167.8 MB + write 4.8 MB), profiles/r01_decode_peaks_ncu_details.txt"},
+                       "peaks_kernel_only": {"us": 33.18, "achieved": 5057.0, "frac": round(5057.0 / hbm, 3), "traffic": 171.4e6,
+                                             "source": "ncu --set full of peaks_fast_kernel (gpu__time_duration, dram__bytes_read 167.8 MB + write 3.6 MB), profiles/r01_decode_peaks_ncu_details.txt"},
                        "algorithmic_bytes_per_launch": d_bytes}
         del heats, dgraph
         # ---- cpu baseline: oracle port on the host cores, bounded sample ---------------------------------------
