@@ -964,13 +964,15 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   plan_rows_mode(op, planes, d.cin, d.stride, !dst.fp32_nchw, e->precision);
   // CTA pair (cta_group::2): Cout tiles of 256 in split precision with the separate correction accumulator
   static const bool pair_on = [] { const char* v = getenv("CNL_PAIR"); return !(v && atoi(v) == 0); }();
+  static const int pair_min_tiles = [] { const char* v = getenv("CNL_PAIR_MIN_TILES"); return v ? atoi(v) : 1024; }();   // tests lower it
   op.pair = 0;
   op.stage_depth = 1;
   // Cout tiles of 128 as pairs (CNL_PAIR128=1) measure 4 % SLOWER than the single-CTA [hi|lo] form: there the A operand's
   // shared-memory read (streamed twice instead of three times) matters more than the fill traffic
   static const bool pair128 = [] { const char* v = getenv("CNL_PAIR128"); return v && atoi(v) != 0; }();
   if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && (op.n_tile == 256 || (op.n_tile == 128 && pair128)) && !op.rows && !dst.fp32_nchw &&
-      op.cluster == 1 && e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= 1024) {     // short launches (layer3/4) measure 5-7 % slower as pairs
+      op.cluster == 1 && e->batch * op.tiles_w * op.tiles_h >= 2 &&
+      e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= pair_min_tiles) {     // short launches (layer3/4) measure 5-7 % slower as pairs
     op.pair = 1;
     op.cluster = 2;                                  // launch as clusters of 2; each CTA's weight box is n_tile / 2 rows
     if (op.n_tile == 128) {                          // the pair splits the weight rows, so the [hi|lo] concatenation is not used:

@@ -48,6 +48,23 @@ def test_conv_probes_subset(cuda):
             assert ok, (c["name"], err)
 
 
+def test_cta_pair_conv_probes_small_and_odd(cuda):
+    """The cta_group::2 form on problems far below its production threshold (CNL_PAIR_MIN_TILES=2, own processes because the
+    knob is read once): odd tile counts (the last cluster's peer CTA runs a dummy tile), two Cout tiles, residual, stride 2."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(__file__))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import conv_probe
+    env = dict(os.environ, CNL_PAIR_MIN_TILES="2")
+    idx = [i for i, c in enumerate(conv_probe.PROBES) if c["name"].startswith("pair_")]
+    assert len(idx) == 4
+    for i in idx:
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "conv_probe.py"), str(i)], env=env, capture_output=True,
+                           text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.startswith("OK "), (conv_probe.PROBES[i]["name"], r.stdout[-400:], r.stderr[-400:])
+
+
 @pytest.mark.parametrize("name", list(cases.FORWARD_CASES))
 def test_forward_matches_reference_golden(cuda, name):
     """Head outputs vs the golden produced by the reference's own GenericModel/GenericHead (tests/golden/gen_golden.py)."""

@@ -58,6 +58,12 @@ PROBES = [
     cfg("rows_deconv4_64_w128_split", 64, 64, 4, 1, (24, 128), n=2, deconv=4),
     cfg("rows_deconv3_64_w72_split", 64, 64, 3, 1, (16, 72), n=1, deconv=3),
     cfg("rows_3x3_64_64_up2_w128_split", 64, 64, 3, 1, (16, 128), n=2, up=1),
+    # CTA-pair form (run with CNL_PAIR_MIN_TILES=2 so that these small problems take it): odd tile counts leave the
+    # peer CTA of the last cluster with a dummy tile; two Cout tiles; residual; stride 2
+    cfg("pair_3x3_256_256_odd9tiles_split", 256, 256, 3, 1, (40, 8), n=3),
+    cfg("pair_3x3_256_512_odd3tiles_res_split", 256, 512, 3, 1, (40, 8), n=1, res=1),
+    cfg("pair_3x3s2_256_256_w64_split", 256, 256, 3, 2, 64, n=1),
+    cfg("pair_3x3_512_256_w32_1img_split", 512, 256, 3, 1, 32, n=1),
 ]
 
 
