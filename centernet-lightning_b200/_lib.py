@@ -13,9 +13,9 @@ LIB_PATH = os.environ.get("CNL_LIB") or os.path.join(_HERE, "libcnl_b200.so")
 
 EXPORTS = (
     "cnl_last_error", "cnl_version", "cnl_compiled_sm",
-    "cnl_decode_workspace_bytes", "cnl_decode_detections", "cnl_gather_boxes", "cnl_sigmoid", "cnl_boxes_xyxy_to_xywh",
+    "cnl_decode_workspace_bytes", "cnl_decode_workspace_bytes_k", "cnl_decode_detections", "cnl_decode_detections_packed", "cnl_gather_boxes", "cnl_sigmoid", "cnl_boxes_xyxy_to_xywh",
     "cnl_normalize_images_u8", "cnl_track_workspace_bytes", "cnl_track_cost_matrices",
-    "cnl_engine_create", "cnl_engine_destroy", "cnl_engine_arena_bytes", "cnl_engine_buffer_offset",
+    "cnl_engine_create", "cnl_engine_destroy", "cnl_engine_arena_bytes", "cnl_engine_buffer_offset", "cnl_engine_op_form",
     "cnl_engine_upload", "cnl_engine_forward", "cnl_engine_read_buffer", "cnl_engine_write_buffer",
 )
 
@@ -60,6 +60,15 @@ def load() -> C.CDLL:
         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.cnl_decode_workspace_bytes_k.restype = C.c_size_t
+    lib.cnl_decode_workspace_bytes_k.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.cnl_decode_detections_packed.restype = C.c_int
+    lib.cnl_decode_detections_packed.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+        C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cnl_boxes_xyxy_to_xywh.restype = C.c_int
     lib.cnl_boxes_xyxy_to_xywh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cnl_sigmoid.restype = C.c_int
@@ -84,6 +93,8 @@ def load() -> C.CDLL:
     lib.cnl_engine_arena_bytes.argtypes = [C.c_void_p]
     lib.cnl_engine_buffer_offset.restype = C.c_size_t
     lib.cnl_engine_buffer_offset.argtypes = [C.c_void_p, C.c_int]
+    lib.cnl_engine_op_form.restype = C.c_int
+    lib.cnl_engine_op_form.argtypes = [C.c_void_p, C.c_int]
     lib.cnl_engine_upload.restype = C.c_int
     lib.cnl_engine_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cnl_engine_forward.restype = C.c_int

@@ -1152,6 +1152,12 @@ size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer) {
   return e->bufs[buffer].offset;
 }
 
+int cnl_engine_op_form(const cnl_engine* e, int op) {
+  if (!e || op < 0 || op >= (int)e->ops.size()) return -1;
+  const OpInfo& o = e->ops[op];
+  return (o.rows ? 1 : 0) | (o.pair ? 2 : 0) | (o.corr ? 4 : 0) | (o.cat ? 8 : 0);
+}
+
 int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
   if (!e || !arena) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_upload: null argument");
   if (reinterpret_cast<uintptr_t>(arena) & 1023) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_upload: arena must be 1024-byte aligned");

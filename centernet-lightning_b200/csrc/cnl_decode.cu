@@ -16,7 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
-#include <cuda.h>
+#include <type_traits>
 #include "cnl_common.h"
 
 namespace cnl {
@@ -38,13 +38,28 @@ int fail(int code, const char* fmt, ...) {
 // The logistic the from_logits path specifies: three separately rounded fp32 operations.
 __device__ __forceinline__ float sigmoid32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// from_logits semantics.  The reference compares PROBABILITIES (centernet.py:252-254).  The logistic is monotone,
-// so the pseudo-NMS and the class arg-max are evaluated on the logits instead (no transcendental in the streaming
-// loop) and only the per-pixel winner is pushed through sigmoid32.  The two orders differ only where fp32 rounding
-// maps distinct logits to one probability; the case that matters in practice is saturation - every logit >= 16.64
-// has probability exactly 1.0f, so the reference sees a plateau there (neighbouring saturated pixels are all kept,
-// the first saturated class wins the label).  Clamping logits at kSatLogit reproduces that plateau exactly.
-constexpr float kSatLogit = 17.0f;
+// from_logits semantics.  The reference compares PROBABILITIES (centernet.py:252-254): a pixel is kept when
+// sigmoid(x) == max over the window of sigmoid(.), and the label is the FIRST class whose kept probability equals the
+// per-pixel maximum.  The logistic is monotone, so sigmoid(window max of the logits) is that window maximum and the
+// streaming pass works on logits: x is a peak iff x == m or sigmoid32(x) == sigmoid32(m), m = window max of the logits.
+// fp32 rounding maps many logits to one probability - 8 consecutive floats at x = 3, 211 at x = 8, every x >= 16.64 to
+// exactly 1.0f - so the second clause is real (two neighbours 8.0 / 8.00001 are BOTH peaks in the reference).  It is
+// evaluated only where m - x is below collapse_thr(m), a cheap conservative bound on the width of such a collapse;
+// the per-pixel maximum is converted to a probability once, at the end of the pass, and everything downstream (histogram,
+// select, ordering) runs on probabilities exactly like the from_logits = 0 entry point.
+//
+// collapse_thr: sigmoid32(x) == sigmoid32(m) with x < m  implies  m - x < collapse_thr(m).  With up to 3 ulp of error per
+// evaluated logistic, equal results mean the true values differ by at most 6 ulp(p): for m >= 0 (p in [0.5,1], ulp 2^-24,
+// slope >= 0.25 e^-m) that is m - x <= 1.43e-6 e^m, for m < 0 (ulp <= 2^-23 p, slope >= p/2) m - x <= 1.43e-6.
+// Returned: 2^-18 * 2^ceil(max(m,0) * log2 e) (>= 2.6x the bound).  Saturated (>= 16.5: p is 1 - 2^-24 or 1) and
+// underflowing (< -80: p is denormal or 0, absolute spacing) logits have no useful bound: +inf, always take the exact test.
+__device__ __forceinline__ float collapse_thr(float m) {
+  if (!(m > -80.0f && m < 16.5f)) return INFINITY;           // also catches NaN
+  const int e = (int)ceilf(fmaxf(m, 0.0f) * 1.4426950f) - 18;
+  return __int_as_float((127 + e) << 23);
+}
+// exact peak test of the from_logits path for a centre x below its window max m
+__device__ __forceinline__ bool same_probability(float x, float m) { return sigmoid32(x) == sigmoid32(m); }
 
 // x: centre value, m: kxk window max (m >= x).  Reference: mask = (maxpool(h) == h); h*mask; max over classes.
 // The streaming pass keeps only the per-pixel MAXIMUM of the masked values (3 ALU ops per element); which class
@@ -58,6 +73,12 @@ __device__ __forceinline__ void masked_max(float& best, float x, float m) {
 }
 template <bool LOGITS>
 __device__ __forceinline__ float best_init() { return LOGITS ? -INFINITY : 0.0f; }
+// value written per pixel: always a probability (0 = no peak, as h*mask leaves it in the reference)
+template <bool LOGITS>
+__device__ __forceinline__ float best_to_prob(float best) {
+  if (!LOGITS) return best;
+  return (best == -INFINITY) ? 0.0f : sigmoid32(best);
+}
 
 __device__ __forceinline__ uint32_t sortable_key(float f) {       // larger float <=> larger key (NaN-free input)
   uint32_t b = __float_as_uint(f);
@@ -71,18 +92,17 @@ constexpr int kHistBins = 4096;             // per-image histogram of candidate 
 constexpr int kHistShift = 20;
 
 // Histogram update of one candidate per lane (whole warp, converged).  Pixels without any peak keep the initial value
-// (-inf / 0): they are NOT counted - smooth maps have thousands of them per image and they would all hit one address;
+// (probability 0): they are NOT counted - smooth maps have thousands of them per image and they would all hit one address;
 // the select kernel recovers their number as H*W minus the histogram total.  The remaining lanes are aggregated per
 // bin with match.any, so a warp issues one atomic per distinct bin.
-template <bool LOGITS>
 __device__ __forceinline__ void hist_add(unsigned int* hist_img, float v, bool valid) {
-  const bool counted = valid && (LOGITS ? (v != -INFINITY) : (v != 0.0f));
+  const bool counted = valid && (v != 0.0f);
   const uint32_t bin = sortable_key(v) >> kHistShift;
   const unsigned peers = __match_any_sync(0xffffffffu, counted ? bin : 0xffffffffu);
   if (counted && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist_img + bin, (unsigned)__popc(peers));
 }
 // bin that holds the uncounted "no peak" candidates
-__host__ __device__ constexpr int no_peak_bin(bool logits) { return logits ? 7 : 2048; }   // key(-inf) = 0x007fffff, key(0.f) = 0x80000000
+constexpr int kNoPeakBin = 2048;             // key(0.f) = 0x80000000
 
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1a: fast streaming peaks kernel (W % 4 == 0).  One warp = RxTW pixel strip x one class group.
@@ -102,6 +122,9 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 // Class loop of one warp: rows [r0-P, r0+R+P) x columns [x0-P, x0+4*VEC+P) of classes [c_begin, c_end).
 // A lane owns 4*VEC consecutive columns (VEC float4 loads per row), the warp a tile of 128*VEC columns.
 // EDGE=false is the interior fast path (every row and column of the strip is inside the map: no predicates).
+// LOGITS: the fast pass applies the x == m test and tracks the smallest non-zero gap m - x it saw; only when some lane's
+// gap is below collapse_thr (a near tie: see the semantics note above) the class is walked a second time with the exact
+// probability test for the centres below their window max.
 template <int P, bool LOGITS, int R, bool MT, bool EDGE, int VEC>
 __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base, size_t plane, int c_begin, int c_end,
                                                  int H, int W, int r0, int x0, int lane,
@@ -122,113 +145,119 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
   for (int c = c_begin; c < c_end; ++c) {
     const float* pl = base + (size_t)c * plane;
     float4 v[ROWS][VEC];
+    float hx[ROWS][PH];
+    auto load_strip = [&]() {
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j)
+      for (int j = 0; j < ROWS; ++j)
 #pragma unroll
-      for (int u = 0; u < VEC; ++u) {
-        if (EDGE) v[j][u] = (row_ok[j] && col_ok[u]) ? ld_stream4(pl + (long long)j * W + 4 * u) : make_float4(NEG, NEG, NEG, NEG);
-        else      v[j][u] = ld_stream4(pl + (long long)j * W + 4 * u);
+        for (int u = 0; u < VEC; ++u) {
+          if (EDGE) v[j][u] = (row_ok[j] && col_ok[u]) ? ld_stream4(pl + (long long)j * W + 4 * u) : make_float4(NEG, NEG, NEG, NEG);
+          else      v[j][u] = ld_stream4(pl + (long long)j * W + 4 * u);
+        }
+      // Halo columns of neighbouring column tiles (rows wider than one warp tile).  The neighbour shuffles below are
+      // rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the right" shuffle
+      // are free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
+      if constexpr (P > 0 && MT) {
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j)
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            hx[j][q] = NEG;
+            const int xt = (lane == 31) ? (x0 - 31 * NC - 1 - q) : (x0 + 32 * NC + q);     // tile's first column - 1 - q / last + 1 + q
+            if ((lane == 0 || lane == 31) && row_ok[j] && xt >= 0 && xt < W) hx[j][q] = __ldg(pl + (long long)j * W + (xt - x0));
+          }
       }
-    if (LOGITS) {
-      // saturation clamp (see kSatLogit) only when some logit of this warp's rows reaches it - rare in practice
+    };
+    load_strip();
+    float thr = 0.0f;
+    if constexpr (LOGITS && P > 0) {
+      // largest logit this lane can see as a window max: its own columns, its neighbour lanes' and the halo columns
       float4 t4 = v[0][0];
 #pragma unroll
       for (int j = 0; j < ROWS; ++j)
 #pragma unroll
         for (int u = 0; u < VEC; ++u) t4 = max4(t4, v[j][u]);
-      const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
-      if (__any_sync(0xffffffffu, tmax >= kSatLogit)) {
+      float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
+      if constexpr (MT) {
 #pragma unroll
         for (int j = 0; j < ROWS; ++j)
 #pragma unroll
-          for (int u = 0; u < VEC; ++u)
-            v[j][u] = make_float4(fminf(v[j][u].x, kSatLogit), fminf(v[j][u].y, kSatLogit), fminf(v[j][u].z, kSatLogit),
-                                  fminf(v[j][u].w, kSatLogit));
+          for (int q = 0; q < P; ++q) tmax = fmaxf(tmax, hx[j][q]);
       }
+      const float tl = __shfl_sync(0xffffffffu, tmax, (lane + 31) & 31), tr = __shfl_sync(0xffffffffu, tmax, (lane + 1) & 31);
+      thr = collapse_thr(fmaxf(tmax, fmaxf(tl, tr)));
     }
-    // Halo columns of neighbouring column tiles (rows wider than one warp tile).  The neighbour shuffles below are
-    // rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the right" shuffle
-    // are free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
-    float hx[ROWS][PH];
-    if constexpr (P > 0 && MT) {
+    // one walk over the strip's rows; EXACT = false: x == m test (+ smallest non-zero gap), EXACT = true: probability test
+    // for the centres that are below their window max by less than thr
+    float gap = INFINITY;
+    auto walk = [&](auto exact_tag, float thr) {
+      constexpr bool EXACT = decltype(exact_tag)::value;
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j)
+      for (int i = 0; i < R; ++i) {
+        // vertical max over the window rows
+        float4 vm[VEC];
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-          hx[j][q] = NEG;
-          const int xt = (lane == 31) ? (x0 - 31 * NC - 1 - q) : (x0 + 32 * NC + q);     // tile's first column - 1 - q / last + 1 + q
-          if ((lane == 0 || lane == 31) && row_ok[j] && xt >= 0 && xt < W) {
-            float t = __ldg(pl + (long long)j * W + (xt - x0));
-            hx[j][q] = LOGITS ? fminf(t, kSatLogit) : t;
-          }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-      // vertical max over the window rows
-      float4 vm[VEC];
-#pragma unroll
-      for (int u = 0; u < VEC; ++u) vm[u] = v[i][u];
-      float vh[PH];
-      if constexpr (P > 0 && MT) {
-#pragma unroll
-        for (int q = 0; q < P; ++q) vh[q] = hx[i][q];
-      }
-#pragma unroll
-      for (int j = 1; j <= 2 * P; ++j) {
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) vm[u] = max4(vm[u], v[i + j][u]);
+        for (int u = 0; u < VEC; ++u) vm[u] = v[i][u];
+        float vh[PH];
         if constexpr (P > 0 && MT) {
 #pragma unroll
-          for (int q = 0; q < P; ++q) vh[q] = fmaxf(vh[q], hx[i + j][q]);
+          for (int q = 0; q < P; ++q) vh[q] = hx[i][q];
+        }
+#pragma unroll
+        for (int j = 1; j <= 2 * P; ++j) {
+#pragma unroll
+          for (int u = 0; u < VEC; ++u) vm[u] = max4(vm[u], v[i + j][u]);
+          if constexpr (P > 0 && MT) {
+#pragma unroll
+            for (int q = 0; q < P; ++q) vh[q] = fmaxf(vh[q], hx[i + j][q]);
+          }
+        }
+        // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+NC-1] own, e[P+NC..] right neighbours
+        float e[NC + 2 * P];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+          e[P + 4 * u + 0] = vm[u].x; e[P + 4 * u + 1] = vm[u].y; e[P + 4 * u + 2] = vm[u].z; e[P + 4 * u + 3] = vm[u].w;
+        }
+        if constexpr (P > 0) {
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            // q-th column to the left of x0 is the (NC-1-q)-th column of lane-1; to the right of x0+NC-1 it is column q of lane+1
+            float src_l = e[P + NC - 1 - q], src_r = e[P + q];
+            if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
+            float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
+            float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
+            if constexpr (!MT) { fl += edge_l; fr += edge_r; }      // -inf beyond the row ends (FADD: keeps the ALU pipe free)
+            e[P - 1 - q] = fl;
+            e[P + NC + q] = fr;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+          const float ctr[4] = {v[i + P][u].x, v[i + P][u].y, v[i + P][u].z, v[i + P][u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float m = e[4 * u + j];
+#pragma unroll
+            for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[4 * u + j + q]);
+            if constexpr (!EXACT) {
+              masked_max<LOGITS>(best[i][4 * u + j], ctr[j], m);
+              if constexpr (LOGITS && P > 0) gap = fminf(gap, (ctr[j] == m) ? INFINITY : m - ctr[j]);
+            } else {
+              // (an out-of-map centre is -inf: m - ctr = inf or NaN, never below thr)
+              if (ctr[j] != m && m - ctr[j] < thr && same_probability(ctr[j], m)) best[i][4 * u + j] = fmaxf(best[i][4 * u + j], ctr[j]);
+            }
+          }
         }
       }
-      // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+NC-1] own, e[P+NC..] right neighbours
-      float e[NC + 2 * P];
-#pragma unroll
-      for (int u = 0; u < VEC; ++u) {
-        e[P + 4 * u + 0] = vm[u].x; e[P + 4 * u + 1] = vm[u].y; e[P + 4 * u + 2] = vm[u].z; e[P + 4 * u + 3] = vm[u].w;
-      }
-      if constexpr (P > 0) {
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-          // q-th column to the left of x0 is the (NC-1-q)-th column of lane-1; to the right of x0+NC-1 it is column q of lane+1
-          float src_l = e[P + NC - 1 - q], src_r = e[P + q];
-          if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
-          float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
-          float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
-          if constexpr (!MT) { fl += edge_l; fr += edge_r; }      // -inf beyond the row ends (FADD: keeps the ALU pipe free)
-          e[P - 1 - q] = fl;
-          e[P + NC + q] = fr;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < VEC; ++u) {
-        const float ctr[4] = {v[i + P][u].x, v[i + P][u].y, v[i + P][u].z, v[i + P][u].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float m = e[4 * u + j];
-#pragma unroll
-          for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[4 * u + j + q]);
-          masked_max<LOGITS>(best[i][4 * u + j], ctr[j], m);
-        }
+    };
+    walk(std::false_type{}, 0.0f);
+    if constexpr (LOGITS && P > 0) {
+      if (__any_sync(0xffffffffu, gap < thr)) {      // near tie somewhere in this warp's strip: rare
+        load_strip();                                // (re-read from L2: the strip's registers were released during the walk)
+        walk(std::true_type{}, thr);
       }
     }
   }
-}
-
-// ---- mbarrier helpers (used by the TMA-fed variant below) ------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "RING_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra RING_DONE_%=;\n"
-      "bra RING_WAIT_%=;\n"
-      "RING_DONE_%=:\n"
-      "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
 }
 
 template <int P, bool LOGITS, int R, int G, bool MT, int VEC>
@@ -284,151 +313,31 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uin
       for (int j = 0; j < 4; ++j) {
         if (G > 1) {
           bv[j] = s_v[0][i][lane * NC + 4 * u + j];
+          uint32_t gj = 0;
 #pragma unroll
           for (int gg = 1; gg < G; ++gg) {
             const float ov = s_v[gg][i][lane * NC + 4 * u + j];
-            if (ov > bv[j]) { bv[j] = ov; grp = (grp & ~(0xffu << (8 * j))) | ((uint32_t)gg << (8 * j)); }
+            if (ov > bv[j]) { bv[j] = ov; gj = (uint32_t)gg; }
           }
+          if (LOGITS) {
+            // an EARLIER group whose best logit is smaller but may round to the same probability owns the first maximal
+            // class (reference: first class whose kept probability equals the maximum): group unknown, scan every class
+            const float thr = collapse_thr(bv[j]);
+#pragma unroll
+            for (int gg = 0; gg < G - 1; ++gg)
+              if ((uint32_t)gg < gj && bv[j] - s_v[gg][i][lane * NC + 4 * u + j] < thr) gj = 0xffu;
+          }
+          grp |= gj << (8 * j);
         } else {
           bv[j] = best[i][4 * u + j];
         }
-        hist_add<LOGITS>(hist + (size_t)n * kHistBins, bv[j], ok);
+        bv[j] = best_to_prob<LOGITS>(bv[j]);
+        hist_add(hist + (size_t)n * kHistBins, bv[j], ok);
       }
       if (ok) {
         *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + xu) = grp;
         *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + xu) = make_float4(bv[0], bv[1], bv[2], bv[3]);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Kernel 1a': TMA-fed peaks kernel for the common geometry (W == 128, nms 3x3, C % 4 == 0).
-//   CTA = one 4-row strip of one image, 4 warps.  A 2-stage shared-memory ring is filled by ONE 3-D tensor-map load
-//   per stage: box {128 columns, 6 rows, 4 classes} = 12 KB (rows r0-1..r0+4 of four consecutive class planes).  Warp g
-//   consumes class 4*it+g of every stage (pulls it into registers at once, so the stage is refilled immediately).
-//   Bytes in flight per SM are set by the ring (2 stages x 12 KB x 7 CTAs = 168 KB) instead of by registers, and the load path costs one elected-thread instruction per 12 KB.
-//   Strips touching the top/bottom border (-inf padding, which TMA zero-fill cannot express) use the LDG loop.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kTmaStages = 2;
-constexpr int kTmaClasses = 4;       // classes per stage = warps per CTA
-
-template <bool LOGITS>
-__global__ void __launch_bounds__(128, 7)
-peaks_tma_kernel(const __grid_constant__ CUtensorMap heat_map, const float* __restrict__ heat, float* __restrict__ cbest,
-                 uint8_t* __restrict__ cgroup, unsigned int* __restrict__ hist, int C, int H, int W) {
-  constexpr int P = 1, R = 4, G = 4, ROWS = R + 2 * P;
-  constexpr int kStageFloats = kTmaClasses * ROWS * kTW;             // 3072 floats = 12 KB
-  __shared__ __align__(128) float s_ring[kTmaStages * kStageFloats];
-  __shared__ __align__(8) uint64_t s_full[kTmaStages];
-  __shared__ __align__(8) uint64_t s_empty[kTmaStages];
-  const int lane = threadIdx.x & 31;
-  const int g = threadIdx.x >> 5;
-  const int n = blockIdx.z;
-  const int r0 = blockIdx.y * R;
-  const int x0 = lane * 4;
-  const size_t plane = (size_t)H * W;
-  const float NEG = -INFINITY;
-  const float edge_l = (lane == 0) ? NEG : 0.0f, edge_r = (lane == 31) ? NEG : 0.0f;
-
-  float best[R][4];
-#pragma unroll
-  for (int i = 0; i < R; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) best[i][j] = best_init<LOGITS>();
-
-  const bool interior = (r0 - P >= 0) && (r0 + R + P <= H);          // block-uniform
-  if (interior) {
-    const int n_it = C / kTmaClasses;
-    if (threadIdx.x == 0) {
-      for (int s2 = 0; s2 < kTmaStages; ++s2) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_full[s2])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&s_empty[s2])), "r"(G) : "memory");
-      }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto arm = [&](int it) {
-      const int s2 = it % kTmaStages;
-      const uint32_t bar = smem_addr_u32(&s_full[s2]);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageFloats * 4) : "memory");
-      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                   ::"r"(smem_addr_u32(s_ring + s2 * kStageFloats)), "l"(reinterpret_cast<uint64_t>(&heat_map)), "r"(bar),
-                     "r"(0), "r"(r0 - P), "r"(n * C + it * kTmaClasses) : "memory");
-    };
-    if (threadIdx.x == 0) {
-      arm(0);
-      if (n_it > 1) arm(1);
-    }
-#pragma unroll 1
-    for (int it = 0; it < n_it; ++it) {
-      const int s2 = it % kTmaStages;
-      ring_wait(&s_full[s2], (it / kTmaStages) & 1);
-      const float* st = s_ring + s2 * kStageFloats + g * ROWS * kTW + lane * 4;
-      float4 v[ROWS];
-#pragma unroll
-      for (int j = 0; j < ROWS; ++j) v[j] = *reinterpret_cast<const float4*>(st + j * kTW);
-      float4 vm[R];
-#pragma unroll
-      for (int i = 0; i < R; ++i) vm[i] = max4(max4(v[i], v[i + 1]), v[i + 2]);
-      if (LOGITS) {
-        float4 t4 = max4(max4(vm[0], vm[1]), max4(vm[2], vm[3]));
-        const float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
-        if (__any_sync(0xffffffffu, tmax >= kSatLogit)) {            // saturation clamp, rare (see kSatLogit)
-#pragma unroll
-          for (int j = 0; j < ROWS; ++j)
-            v[j] = make_float4(fminf(v[j].x, kSatLogit), fminf(v[j].y, kSatLogit), fminf(v[j].z, kSatLogit), fminf(v[j].w, kSatLogit));
-#pragma unroll
-          for (int i = 0; i < R; ++i) vm[i] = max4(max4(v[i], v[i + 1]), v[i + 2]);
-        }
-      }
-      __syncwarp();                                                  // every lane's stage reads are consumed (vm depends on them)
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(&s_empty[s2])) : "memory");
-      // producer duty of thread 0: once all 4 warps have pulled this stage into registers, refill it two classes-groups ahead
-      if (threadIdx.x == 0 && it + kTmaStages < n_it) {
-        ring_wait(&s_empty[s2], (it / kTmaStages) & 1);
-        arm(it + kTmaStages);
-      }
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        float fl = __shfl_sync(0xffffffffu, vm[i].w, (lane + 31) & 31);
-        float fr = __shfl_sync(0xffffffffu, vm[i].x, (lane + 1) & 31);
-        fl += edge_l;
-        fr += edge_r;
-        const float e[6] = {fl, vm[i].x, vm[i].y, vm[i].z, vm[i].w, fr};
-        const float ctr[4] = {v[i + 1].x, v[i + 1].y, v[i + 1].z, v[i + 1].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) masked_max<LOGITS>(best[i][j], ctr[j], fmaxf(fmaxf(e[j], e[j + 1]), e[j + 2]));
-      }
-    }
-  } else {
-    const int cg = (C + G - 1) / G;
-    const int c_begin = g * cg, c_end = min(C, c_begin + cg);
-    const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
-    peaks_class_loop<P, LOGITS, R, false, true, 1>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
-  }
-
-  // merge the 4 warps' maxima through shared memory (aliases the ring)
-  __syncthreads();
-  float (*s_v)[R][kTW] = reinterpret_cast<float (*)[R][kTW]>(s_ring);
-#pragma unroll
-  for (int i = 0; i < R; ++i)
-    *reinterpret_cast<float4*>(&s_v[g][i][lane * 4]) = make_float4(best[i][0], best[i][1], best[i][2], best[i][3]);
-  __syncthreads();
-  {
-    const int i = g;                                                 // warp g finishes row g (R == G)
-    const int r = r0 + i;
-    if (r < H) {
-      float bv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bv[j] = s_v[0][i][lane * 4 + j];
-#pragma unroll
-        for (int gg = 1; gg < G; ++gg) bv[j] = fmaxf(bv[j], s_v[gg][i][lane * 4 + j]);
-        hist_add<LOGITS>(hist + (size_t)n * kHistBins, bv[j], true);
-      }
-      *reinterpret_cast<float4*>(cbest + (size_t)n * plane + (size_t)r * W + x0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-      *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + x0) = 0xffffffffu;   // classes interleaved: scan all
     }
   }
 }
@@ -451,16 +360,20 @@ peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cbest, 
   const int x_lo = max(0, x - P), x_hi = min(W - 1, x + P);
   for (int c = 0; c < C; ++c) {
     const float* pl = img + (size_t)c * plane;
-    float ctr = __ldg(pl + (size_t)y * W + x);
+    const float ctr = __ldg(pl + (size_t)y * W + x);
     float m = ctr;
     for (int yy = y_lo; yy <= y_hi; ++yy)
       for (int xx = x_lo; xx <= x_hi; ++xx) m = fmaxf(m, __ldg(pl + (size_t)yy * W + xx));
-    if (LOGITS) { ctr = fminf(ctr, kSatLogit); m = fminf(m, kSatLogit); }
-    masked_max<LOGITS>(best, ctr, m);
+    if (LOGITS) {
+      if (ctr == m || (m - ctr < collapse_thr(m) && same_probability(ctr, m))) best = fmaxf(best, ctr);
+    } else {
+      masked_max<LOGITS>(best, ctr, m);
+    }
   }
+  best = best_to_prob<LOGITS>(best);
   cbest[(size_t)n * plane + (size_t)y * W + x] = best;
   cgroup[(size_t)n * plane + (size_t)y * W + x] = 0xff;
-  if (LOGITS ? (best != -INFINITY) : (best != 0.0f))          // no-peak pixels are not counted (see hist_add)
+  if (best != 0.0f)          // no-peak pixels are not counted (see hist_add)
     atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(best) >> kHistShift), 1u);
 }
 
@@ -478,7 +391,6 @@ constexpr int kListCap = 2048;
 constexpr int kBins = 2048;
 constexpr int kSubShift = kHistShift - 11;   // second-level digit: the next 11 key bits
 constexpr int kRefineAbove = 256;
-constexpr int kBoxPrefetchK = 256;           // box values of up to this many winners are prefetched during the label recovery
 constexpr int kLabelBatch = 3;               // classes per lane and batch in the label recovery (8 lanes x 3 = 24 classes at once)            // sort directly when bin_k-and-above holds at most this many
 
 // inclusive block scan over kSelThreads ints (warp shuffles + one smem hop)
@@ -577,6 +489,8 @@ struct DecodeParams {
   int H, W, E, k;
   int normalize, box_log; float mult; float stride_f;
   float* boxes; float* scores; long long* labels; long long* indices; float* emb;
+  float* packed; int packed_w;                       // optional packed rows [x1,y1,x2,y2,score,index bits,label lo,label hi,emb...]
+  unsigned long long* sortbuf; int sort_cap;         // k > kMaxK: per-image global sort buffer of sort_cap = pow2(H*W) entries
 };
 
 __device__ __forceinline__ unsigned long long pack_entry(uint32_t key, int idx) {
@@ -699,7 +613,6 @@ select_gather_kernel(DecodeParams p) {
   // have to fetch it from global memory first (one dependent round trip less)
   __shared__ uint8_t s_grp_in[kListCap];
   __shared__ uint8_t s_grp_sorted[kSelThreads];
-  __shared__ float s_boxraw[4 * kBoxPrefetchK];       // raw box-map values of the winners, fetched together with their class values
 
   const int n = blockIdx.x;
   const int tid = threadIdx.x;
@@ -788,10 +701,21 @@ select_gather_kernel(DecodeParams p) {
     if (tid == kSelThreads - 1) s_total = total;
     __syncthreads();
     const int missing = HW - s_total;
-    const int nb = no_peak_bin(p.from_logits != 0);
+    const int nb = kNoPeakBin;
     const int owner = (kHistBins - 1 - nb) >> 2, slot = (kHistBins - 1 - nb) & 3;            // thread / position of that bin
     if (tid == owner) { cnt[slot] += missing; sum4 += missing; }
   }
+  const unsigned long long* s_sorted = s_list;
+  bool have_grp = false;                             // s_grp_sorted[j] = class group of winner j
+  if (k > kMaxK) {
+    // More winners than the shared-memory lists hold (the reference accepts any k <= H*W, centernet.py:259): sort ALL
+    // candidates of the image in a global buffer (L2-resident; one CTA, so __syncthreads orders the passes).  Rare path.
+    unsigned long long* buf = p.sortbuf + (size_t)n * p.sort_cap;
+    for (int i = tid; i < p.sort_cap; i += kSelThreads) buf[i] = (i < HW) ? pack_entry(sortable_key(sc[i]), i) : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(buf, nullptr, p.sort_cap, tid);
+    s_sorted = buf;
+  } else {
   int incl = block_inclusive_scan(sum4, s_warp);
   int run = incl - sum4;
   if (run < k && k <= incl) {                    // exactly one thread: the k-th largest lies in one of its bins
@@ -851,9 +775,7 @@ select_gather_kernel(DecodeParams p) {
     n_sort = k;
   }
   // ---- sort, descending -------------------------------------------------------------------------------------
-  const unsigned long long* s_sorted = s_list;
   __syncthreads();
-  bool have_grp = false;                             // s_grp_sorted[j] = class group of winner j
   if (n_sort <= kSelThreads) {                       // the usual case: k .. a few hundred collected candidates
     have_grp = CACHE && done;
     rank_sort_desc<uint8_t>(s_list, have_grp ? s_grp_in : nullptr, n_sort, s_list + kSelThreads, s_grp_sorted, tid);
@@ -865,18 +787,16 @@ select_gather_kernel(DecodeParams p) {
     __syncthreads();
     bitonic_sort_desc(s_list, nullptr, kp, tid);
   }
+  }   // k <= kMaxK
 
-  // ---- label recovery + score for the k winners ---------------------------------------------------------------
+  // ---- label recovery, box decode and output of the k winners ---------------------------------------------------------------
   // Reference: labels = argmax over classes of the MASKED map (first maximal class).  For a winner with best value v
   // that is the first class c with value(c) == v that is a kxk peak.  8 lanes share one winner: each loads C/8
   // classes (independent loads, one latency round trip); a second look at the 3x3 window is needed only when
   // several classes hold exactly the same value.
-  __shared__ uint32_t s_label[kMaxK];
-  unsigned long long* s_out = reinterpret_cast<unsigned long long*>(s_hist);   // 8 KB = kMaxK entries; histogram no longer needed
   const size_t plane = (size_t)HW;
   const float* img = p.heat + (size_t)n * p.C * plane;
   const int sub = tid & 7;
-  const bool box_pre = (p.box != nullptr) && (k <= kBoxPrefetchK);
   const int scan_len = (p.group_classes > 0) ? p.group_classes : p.C;       // classes to re-read per winner (CTA-uniform)
   for (int j0 = 0; j0 < k; j0 += kSelThreads / 8) {
     const int j = j0 + (tid >> 3);
@@ -889,7 +809,7 @@ select_gather_kernel(DecodeParams p) {
       v = key_to_float((uint32_t)(w >> 32));
     }
     int first = 0x7fffffff;
-    const bool trivial = p.from_logits ? (v == -INFINITY) : (v == 0.0f);     // all-zero column: argmax is class 0
+    const bool trivial = (v == 0.0f);                                        // all-zero column: argmax is class 0
     // kernel 1 recorded which class group attained the maximum: only those classes are re-read (the C planes of one
     // pixel are 4*H*W bytes apart - same DRAM bank - so every class read costs a row activation)
     int c_lo = 0, c_hi = p.C;
@@ -899,7 +819,7 @@ select_gather_kernel(DecodeParams p) {
     }
     // the winners' box-map values travel with their class values (independent loads, same round trip)
     float braw = 0.f;
-    if (box_pre && act && sub < 4) braw = __ldg(p.box + ((size_t)n * 4 + sub) * plane + idx);
+    if (p.box != nullptr && act && sub < 4) braw = __ldg(p.box + ((size_t)n * 4 + sub) * plane + idx);
     const bool multi_batch = scan_len > 8 * kLabelBatch;
     for (int off = 0; off < scan_len; off += 8 * kLabelBatch) {              // uniform trip count for the whole CTA
       float xv[kLabelBatch];
@@ -909,11 +829,14 @@ select_gather_kernel(DecodeParams p) {
         const int c = c_lo + off + sub + 8 * q;
         xv[q] = (act && !trivial && c < c_hi) ? __ldg(img + (size_t)c * plane + idx) : NAN;
       }
+      // from_logits: the candidate is a probability, the map holds logits - a class matches when its logit rounds to
+      // that probability (distinct logits can: see the semantics note at the top)
+      bool hit[kLabelBatch];
 #pragma unroll
       for (int q = 0; q < kLabelBatch; ++q) {
-        if (p.from_logits) xv[q] = fminf(xv[q], kSatLogit);                  // (padding lanes are excluded by the c < c_hi test)
         const int c = c_lo + off + sub + 8 * q;
-        nmatch += (act && !trivial && c < c_hi && xv[q] == v) ? 1 : 0;
+        hit[q] = act && !trivial && c < c_hi && ((p.from_logits ? sigmoid32(xv[q]) : xv[q]) == v);   // (padding lanes hold NaN)
+        nmatch += hit[q] ? 1 : 0;
       }
       int total = nmatch;                                                     // matches among the 8 lanes of this winner
 #pragma unroll
@@ -921,71 +844,55 @@ select_gather_kernel(DecodeParams p) {
 #pragma unroll
       for (int q = 0; q < kLabelBatch; ++q) {
         const int c = c_lo + off + sub + 8 * q;
-        if (!(act && !trivial && c < c_hi && xv[q] == v) || c >= first) continue;
+        if (!hit[q] || c >= first) continue;
         bool peak = true;                                                     // a unique match IS the peak that produced v
         if (total > 1 || multi_batch) {
           const int y = idx / p.W, xx0 = idx - y * p.W;
           float m = xv[q];
           for (int yy = max(0, y - p.P); yy <= min(p.H - 1, y + p.P); ++yy)
             for (int xx = max(0, xx0 - p.P); xx <= min(p.W - 1, xx0 + p.P); ++xx) {
-              float t = __ldg(img + (size_t)c * plane + (size_t)yy * p.W + xx);
-              if (p.from_logits) t = fminf(t, kSatLogit);
-              m = fmaxf(m, t);
+              m = fmaxf(m, __ldg(img + (size_t)c * plane + (size_t)yy * p.W + xx));
             }
-          peak = (m == xv[q]);
+          peak = (m == xv[q]) || (p.from_logits && sigmoid32(m) == v);      // kept iff its probability is the window's maximum
         }
         if (peak) first = c;
       }
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-    if (box_pre && act && sub < 4) s_boxraw[4 * j + sub] = braw;
+    // lanes 0..3 of the winner hold its four box-map values: hand them to lane 0, which decodes and writes the row
+    const int seg = (tid & 31) & ~7;
+    const float g0 = __shfl_sync(0xffffffffu, braw, seg), g1 = __shfl_sync(0xffffffffu, braw, seg + 1);
+    const float g2 = __shfl_sync(0xffffffffu, braw, seg + 2), g3 = __shfl_sync(0xffffffffu, braw, seg + 3);
     if (act && sub == 0) {
-      float score = p.from_logits ? sigmoid32(v) : v;
-      uint32_t label = (first == 0x7fffffff) ? 0u : (uint32_t)first;
-      if (score == 0.0f) label = 0u;                       // underflowed / zero candidates arg-max to class 0
-      s_label[j] = label | ((uint32_t)j << 16);            // class (< 65536) + position before the re-sort (< 1024)
-      // canonical output order is (score desc, index asc): distinct logits can round to one probability, so re-key
-      // (into a second list: the first one is still being read by the other lanes of this winner)
-      s_out[j] = pack_entry(sortable_key(score), idx);
+      long long label = (first == 0x7fffffff) ? 0 : (long long)first;
+      if (v == 0.0f) label = 0;                            // underflowed / zero candidates arg-max to class 0
+      const size_t o = (size_t)n * k + j;                  // the winners are in canonical order (probability desc, index asc)
+      p.scores[o] = v;
+      p.indices[o] = idx;
+      p.labels[o] = label;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.box != nullptr) {
+        const float g[4] = {g0, g1, g2, g3};
+        b4 = decode_box_from(g, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
+        *reinterpret_cast<float4*>(p.boxes + o * 4) = b4;
+      }
+      if (p.packed != nullptr) {                           // row for the cross-rank all_gather (bit-exact integer lanes)
+        float* row = p.packed + o * (size_t)p.packed_w;
+        *reinterpret_cast<float4*>(row) = b4;
+        *reinterpret_cast<float4*>(row + 4) = make_float4(v, __int_as_float(idx), __int_as_float((int)(label & 0xffffffffll)),
+                                                          __int_as_float((int)(label >> 32)));
+      }
     }
-  }
-  __syncthreads();
-  const unsigned long long* s_fin = s_out;
-  const uint32_t* s_fin_label = s_label;
-  if (p.from_logits) {                               // s_list is free again: sorted keys in its first half, labels behind
-    uint32_t* lab2 = reinterpret_cast<uint32_t*>(s_list + kSelThreads);
-    rank_sort_desc<uint32_t>(s_out, s_label, k, s_list, lab2, tid);
-    s_fin = s_list;
-    s_fin_label = lab2;
-  }
-
-  // ---- gather + decode -------------------------------------------------------------------------------------
-  for (int j = tid; j < k; j += kSelThreads) {
-    unsigned long long w = s_fin[j];
-    int idx = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
-    size_t o = (size_t)n * k + j;
-    p.scores[o] = key_to_float((uint32_t)(w >> 32));
-    p.indices[o] = idx;
-    const uint32_t lab = s_fin_label[j];
-    p.labels[o] = (long long)(lab & 0xffffu);
-    if (p.box == nullptr) continue;
-    float4 b4;
-    if (box_pre) {
-      const int oj = (int)(lab >> 16);
-      const float g[4] = {s_boxraw[4 * oj], s_boxraw[4 * oj + 1], s_boxraw[4 * oj + 2], s_boxraw[4 * oj + 3]};
-      b4 = decode_box_from(g, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
-    } else {
-      b4 = decode_box(p.box + (size_t)n * 4 * plane, plane, idx, p.H, p.W, p.normalize, p.box_log, p.mult, p.stride_f);
-    }
-    *reinterpret_cast<float4*>(p.boxes + o * 4) = b4;
   }
   if (p.reid != nullptr) {                    // fairmot.py:63-73: emb[n, j, e] = reid[n, e, idx_j]
     const int E = p.E;
     for (int t = tid; t < k * E; t += kSelThreads) {
       int j = t / E, e = t - j * E;
-      int idx = (int)(0xffffffffu - (uint32_t)(s_fin[j] & 0xffffffffull));
-      p.emb[((size_t)n * k + j) * E + e] = __ldg(p.reid + ((size_t)n * E + e) * plane + idx);
+      int idx = (int)(0xffffffffu - (uint32_t)(s_sorted[j] & 0xffffffffull));
+      const float val = __ldg(p.reid + ((size_t)n * E + e) * plane + idx);
+      p.emb[((size_t)n * k + j) * E + e] = val;
+      if (p.packed != nullptr) p.packed[((size_t)n * k + j) * p.packed_w + 8 + e] = val;
     }
   }
 }
@@ -1030,43 +937,10 @@ static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsign
   return launch_fast_rv<P, LOGITS, 4, 1>(heat, cscore, cgroup, hist, N, C, H, W, st);
 }
 
-typedef CUresult (*EncodeTiledFnD)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 3-D fp32 tensor map over the heatmap viewed as [N*C][H][W] with box {128, 6, 4}; false if the driver entry is missing.
-static bool make_heat_map(CUtensorMap* m, const float* heat, int N, int C, int H, int W) {
-  static EncodeTiledFnD fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
-    fn = reinterpret_cast<EncodeTiledFnD>(p);
-  }
-  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * C};
-  cuuint64_t str[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTW, 6, (cuuint32_t)kTmaClasses};
-  cuuint32_t es[3] = {1, 1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(heat), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // returns the number of classes per recorded class group (0 = no group information, scan every class)
 template <bool LOGITS>
 static int launch_peaks(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
                         int P, bool force_generic, cudaStream_t st) {
-  // CNL_PEAKS_TMA=1 selects the TMA-fed kernel (measured 50 us vs 43 us for the register-prefetch kernel at
-  // 32x80x128x128 on B200: the pass is bounded by the 1.5x halo re-reads at L2, not by bytes in flight; kept for tuning).
-  static const int use_tma = (getenv("CNL_PEAKS_TMA") && atoi(getenv("CNL_PEAKS_TMA")) != 0) ? 1 : 0;
-  if (!force_generic && use_tma && P == 1 && W == kTW && H % 4 == 0 && H >= 12 && C % kTmaClasses == 0 &&
-      ((reinterpret_cast<uintptr_t>(heat) & 15) == 0)) {
-    CUtensorMap m;
-    if (make_heat_map(&m, heat, N, C, H, W)) {
-      dim3 grid(1, H / 4, N);
-      peaks_tma_kernel<LOGITS><<<grid, 128, 0, st>>>(m, heat, cscore, cgroup, hist, C, H, W);
-      return 0;
-    }
-  }
   bool fast = !force_generic && (W % 4 == 0) && P <= 2 && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   if (fast) {
     switch (P) {
@@ -1080,6 +954,7 @@ static int launch_peaks(const float* heat, float* cscore, uint8_t* cgroup, unsig
   return 0;
 }
 
+static size_t sort_capacity(int h, int w) { size_t c = 1; while (c < (size_t)h * w) c <<= 1; return c; }
 static size_t hist_bytes(int n) { return align_up((size_t)n * kHistBins * sizeof(unsigned int), 256); }
 static size_t score_bytes(int n, int h, int w) { return align_up((size_t)n * h * w * sizeof(float), 256); }
 
@@ -1098,12 +973,19 @@ size_t cnl_decode_workspace_bytes(int n, int h, int w) {
   return hist_bytes(n) + score_bytes(n, h, w) + align_up((size_t)n * h * w, 256);
 }
 
-int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
-                          int n, int c, int h, int w, int reid_dim,
-                          int from_logits, int nms_kernel, int num_detections,
-                          int normalize_boxes, int box_log, float box_multiplier, int stride,
-                          float* boxes, float* scores, int64_t* labels, int64_t* indices, float* embeddings,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+size_t cnl_decode_workspace_bytes_k(int n, int h, int w, int num_detections) {
+  const size_t base = cnl_decode_workspace_bytes(n, h, w);
+  if (base == 0 || num_detections <= kMaxK) return base;
+  return base + (size_t)n * sort_capacity(h, w) * sizeof(unsigned long long);     // global sort buffer of the large-k path
+}
+
+int cnl_decode_detections_packed(const float* heatmap, const float* box_offsets, const float* reid,
+                                 int n, int c, int h, int w, int reid_dim,
+                                 int from_logits, int nms_kernel, int num_detections,
+                                 int normalize_boxes, int box_log, float box_multiplier, int stride,
+                                 float* boxes, float* scores, int64_t* labels, int64_t* indices, float* embeddings,
+                                 float* packed, int packed_width,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   if (!heatmap || !scores || !labels || !indices || !workspace)
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: null pointer argument");
   if ((box_offsets != nullptr) != (boxes != nullptr))
@@ -1123,13 +1005,13 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   if (num_detections < 1 || (long long)num_detections > (long long)h * w)
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: num_detections=%d must be in 1..H*W=%d (torch.topk raises)",
                 num_detections, h * w);
-  if (num_detections > kMaxK)
-    return fail(CNL_ERR_UNSUPPORTED, "cnl_decode_detections: num_detections=%d exceeds %d", num_detections, kMaxK);
+  if (packed != nullptr && (packed_width != 8 + (reid ? reid_dim : 0) || (packed_width & 3) || (reinterpret_cast<uintptr_t>(packed) & 15)))
+    return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: packed rows are 8 + reid_dim floats (a multiple of 4), 16-byte aligned");
   if ((reid != nullptr) != (embeddings != nullptr) || (reid && reid_dim <= 0))
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: reid, embeddings and reid_dim must be given together");
-  if (workspace_bytes < cnl_decode_workspace_bytes(n, h, w))
-    return fail(CNL_ERR_WORKSPACE, "cnl_decode_detections: workspace %zu < %zu bytes", workspace_bytes,
-                cnl_decode_workspace_bytes(n, h, w));
+  if (workspace_bytes < cnl_decode_workspace_bytes_k(n, h, w, num_detections))
+    return fail(CNL_ERR_WORKSPACE, "cnl_decode_detections: workspace %zu < %zu bytes (cnl_decode_workspace_bytes_k)", workspace_bytes,
+                cnl_decode_workspace_bytes_k(n, h, w, num_detections));
   if (reinterpret_cast<uintptr_t>(workspace) & 255)
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: workspace must be 256-byte aligned");
   if (reinterpret_cast<uintptr_t>(boxes) & 15)
@@ -1155,6 +1037,9 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   p.normalize = normalize_boxes; p.box_log = box_log; p.mult = box_multiplier; p.stride_f = (float)stride;
   p.boxes = boxes; p.scores = scores; p.labels = reinterpret_cast<long long*>(labels);
   p.indices = reinterpret_cast<long long*>(indices); p.emb = embeddings;
+  p.packed = packed; p.packed_w = packed_width;
+  p.sortbuf = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + cnl_decode_workspace_bytes(n, h, w));
+  p.sort_cap = (int)sort_capacity(h, w);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n);
@@ -1171,6 +1056,17 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
   }
   CNL_CUDA_CHECK(cudaGetLastError());
   return CNL_OK;
+}
+
+int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
+                          int n, int c, int h, int w, int reid_dim,
+                          int from_logits, int nms_kernel, int num_detections,
+                          int normalize_boxes, int box_log, float box_multiplier, int stride,
+                          float* boxes, float* scores, int64_t* labels, int64_t* indices, float* embeddings,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  return cnl_decode_detections_packed(heatmap, box_offsets, reid, n, c, h, w, reid_dim, from_logits, nms_kernel, num_detections,
+                                      normalize_boxes, box_log, box_multiplier, stride, boxes, scores, labels, indices, embeddings,
+                                      nullptr, 0, workspace, workspace_bytes, stream);
 }
 
 int cnl_boxes_xyxy_to_xywh(const float* boxes_xyxy, float* boxes_xywh, size_t n_boxes, void* stream) {

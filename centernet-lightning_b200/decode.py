@@ -22,10 +22,14 @@ _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
 def _ws(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
+    """Scratch for the allocating entry points, one per (device, stream): two decodes running concurrently on different
+    streams must not share the histogram / candidate map."""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        ws = torch.empty(max(nbytes, 1 << 20) + 256, dtype=torch.uint8, device=device)
+        ws = ws[(-ws.data_ptr()) % 256:]
         _workspaces[key] = ws
     return ws
 
@@ -45,7 +49,8 @@ def _check_map(name: str, t: torch.Tensor, ndim: int = 4) -> torch.Tensor:
 class DecodeBuffers:
     """Pre-allocated outputs + workspace for one decode shape (used inside CUDA-graph capture: no allocation per call)."""
 
-    def __init__(self, n: int, h: int, w: int, k: int, reid_dim: int, device: torch.device):
+    def __init__(self, n: int, h: int, w: int, k: int, reid_dim: int, device: torch.device,
+                 packed: Optional[torch.Tensor] = None):
         lib = _lib.load()
         self.n, self.h, self.w, self.k, self.e = n, h, w, k, reid_dim
         with torch.cuda.device(device):
@@ -54,9 +59,15 @@ class DecodeBuffers:
             self.indices = torch.empty((n, k), dtype=torch.int64, device=device)
             self.boxes = torch.empty((n, k, 4), dtype=torch.float32, device=device)
             self.emb = torch.empty((n, k, reid_dim), dtype=torch.float32, device=device) if reid_dim else None
-            self.ws = torch.empty(lib.cnl_decode_workspace_bytes(n, h, w) + 256, dtype=torch.uint8, device=device)
+            self.ws = torch.empty(lib.cnl_decode_workspace_bytes_k(n, h, w, k) + 256, dtype=torch.uint8, device=device)
             off = (-self.ws.data_ptr()) % 256
             self.ws = self.ws[off:]
+        # optional packed rows (n, k, 8 + reid_dim) written by the select kernel itself: the send buffer of the cross-rank
+        # all_gather (distributed.DetectionGather), so that no torch kernel has to pack the detections
+        self.packed = packed
+        if packed is not None:
+            if tuple(packed.shape) != (n, k, 8 + reid_dim) or packed.dtype != torch.float32 or not packed.is_contiguous():
+                raise ValueError(f"packed must be a contiguous float32 tensor of shape {(n, k, 8 + reid_dim)}")
         self.clean = False          # True once a decode has run on this workspace: its histogram is left zeroed (no memset needed)
 
     def as_dict(self) -> Dict[str, torch.Tensor]:
@@ -76,12 +87,13 @@ def decode_into(bufs: DecodeBuffers, heatmap: torch.Tensor, box_offsets: torch.T
         raise ValueError("DecodeBuffers were built for another shape")
     flags = int(bool(from_logits)) | (2 if bufs.clean else 0)           # CNL_DECODE_WORKSPACE_CLEAN
     bufs.clean = False
-    st = lib.cnl_decode_detections(
+    st = lib.cnl_decode_detections_packed(
         heatmap.data_ptr(), box_offsets.data_ptr(), reid.data_ptr() if reid is not None else None,
         n, c, h, w, bufs.e if reid is not None else 0, flags, int(nms_kernel), int(num_detections),
         int(bool(normalize_boxes)), int(bool(box_log)), float(box_multiplier), int(stride),
         bufs.boxes.data_ptr(), bufs.scores.data_ptr(), bufs.labels.data_ptr(), bufs.indices.data_ptr(),
         bufs.emb.data_ptr() if (bufs.emb is not None and reid is not None) else None,
+        bufs.packed.data_ptr() if bufs.packed is not None else None, bufs.packed.shape[-1] if bufs.packed is not None else 0,
         bufs.ws.data_ptr(), bufs.ws.numel(), torch.cuda.current_stream(heatmap.device).cuda_stream)
     _lib.check(st, "cnl_decode_detections")
     bufs.clean = True
@@ -142,7 +154,7 @@ def decode_detections(heatmap: torch.Tensor, box_offsets: Optional[torch.Tensor]
         indices = torch.empty((n, k), dtype=torch.int64, device=dev)
         boxes = torch.empty((n, k, 4), dtype=torch.float32, device=dev) if box_offsets is not None else None
         emb = torch.empty((n, k, e), dtype=torch.float32, device=dev) if reid is not None else None
-        nbytes = lib.cnl_decode_workspace_bytes(n, h, w)
+        nbytes = lib.cnl_decode_workspace_bytes_k(n, h, w, k)
         ws = _ws(dev, nbytes)
         st = lib.cnl_decode_detections(
             heatmap.data_ptr(), box_offsets.data_ptr() if box_offsets is not None else None,

@@ -86,21 +86,33 @@ class Engine:
                 raise ValueError(f"image must be {(self.batch, 3, self.height, self.width)}, got {tuple(image.shape)}")
             if image.dtype != torch.float32 or not image.is_cuda or not image.is_contiguous():
                 raise ValueError("image must be a contiguous float32 CUDA tensor (NCHW)")
+        if self.handle is None:
+            raise RuntimeError("this engine was closed (its model's weights were reloaded): ask the model for a new one")
         n = C.c_int(0)
-        st = self.lib.cnl_engine_forward(self.handle, self.arena.data_ptr(), image.data_ptr() if image is not None else None,
-                                         first_op, self.num_ops if last_op is None else last_op,
-                                         torch.cuda.current_stream(self.device).cuda_stream, C.byref(n))
+        with torch.cuda.device(self.device):        # launches go to the engine's device whatever the caller's current one is
+            st = self.lib.cnl_engine_forward(self.handle, self.arena.data_ptr(), image.data_ptr() if image is not None else None,
+                                             first_op, self.num_ops if last_op is None else last_op,
+                                             torch.cuda.current_stream(self.device).cuda_stream, C.byref(n))
         _lib.check(st, "cnl_engine_forward")
         self.last_launches = n.value
         return self.outputs
+
+    def kernel_forms(self) -> Dict[str, str]:
+        """op name -> "rows" (row-rolling A operand) / "pair" (cta_group::2) / "tile" (single-CTA im2col tiles)."""
+        out = {}
+        for i, op in enumerate(self.plan.ops):
+            f = self.lib.cnl_engine_op_form(self.handle, i)
+            out[op.name] = "rows" if f & 1 else ("pair" if f & 2 else "tile")
+        return out
 
     def read_buffer(self, name: str) -> torch.Tensor:
         """(N,C,H,W) fp32 copy of any activation buffer (hi+lo planes summed) - for tests."""
         b = self.plan.buffers[name]
         h, w = self.height // b.stride, self.width // b.stride
         out = torch.empty((self.batch, b.channels, h, w), dtype=torch.float32, device=self.device)
-        st = self.lib.cnl_engine_read_buffer(self.handle, self.arena.data_ptr(), self.buffer_ids[name], out.data_ptr(),
-                                             torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            st = self.lib.cnl_engine_read_buffer(self.handle, self.arena.data_ptr(), self.buffer_ids[name], out.data_ptr(),
+                                                 torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(st, "cnl_engine_read_buffer")
         return out
 
@@ -110,14 +122,16 @@ class Engine:
         value = value.to(device=self.device, dtype=torch.float32).contiguous()
         if tuple(value.shape) != (self.batch, b.channels, h, w):
             raise ValueError(f"{name}: expected {(self.batch, b.channels, h, w)}, got {tuple(value.shape)}")
-        st = self.lib.cnl_engine_write_buffer(self.handle, self.arena.data_ptr(), self.buffer_ids[name], value.data_ptr(),
-                                              torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            st = self.lib.cnl_engine_write_buffer(self.handle, self.arena.data_ptr(), self.buffer_ids[name], value.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(st, "cnl_engine_write_buffer")
 
     def close(self) -> None:
         if getattr(self, "handle", None) is not None:
             self.lib.cnl_engine_destroy(self.handle)
             self.handle = None
+            self.arena = self._raw = None             # release the activation arena with the plan
 
     def __del__(self):
         try:

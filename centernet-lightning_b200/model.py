@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import math
 import os
-from collections import namedtuple
+from collections import OrderedDict, namedtuple
 from types import SimpleNamespace
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -163,14 +163,19 @@ class EngineModel(nn.Module):
         self.backbone_name = backbone_name
         self.neck_name = neck_name
         self.precision = precision
-        self._engines: Dict[Tuple, Engine] = {}
+        # one engine (plan + packed weights + activation arena: 7.6 GB at 32 x 512^2) per input shape, least recently used
+        # evicted beyond `max_engines` (ragged last batches / multi-scale inputs would otherwise accumulate arenas)
+        self._engines: "OrderedDict[Tuple, Engine]" = OrderedDict()
+        self.max_engines = 4
+        self.generation = 0            # bumped whenever the parameters may have changed: keys every cached plan / graph
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
 
     def invalidate(self) -> None:
-        """Drop packed weights / plans (call after changing parameters in place)."""
+        """Drop packed weights / plans (call after changing parameters in place; load_state_dict does it itself)."""
         for e in self._engines.values():
             e.close()
         self._engines.clear()
+        self.generation += 1
 
     def head_names(self) -> List[str]:
         return [n for n, _ in self.heads.named_children()]
@@ -180,12 +185,17 @@ class EngineModel(nn.Module):
         key = (n, h, w, images.device.index, self.precision)
         eng = self._engines.get(key)
         if eng is None:
+            while len(self._engines) >= max(1, self.max_engines):
+                _, old = self._engines.popitem(last=False)
+                old.close()
             names = self.head_names()
             depth = getattr(self.heads, names[0]).depth
             plan = build_plan(self.state_dict(), backbone=self.backbone_name, neck=self.neck_name, head_names=names,
                               head_depth=depth)
             eng = Engine(plan, n, h, w, images.device, precision=self.precision)
             self._engines[key] = eng
+        else:
+            self._engines.move_to_end(key)
         return eng
 
     def forward(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -195,7 +205,9 @@ class EngineModel(nn.Module):
             raise RuntimeError("images are on the CPU: the cnl_b200 forward runs on CUDA (sm_100a) only, there is no fallback")
         images = images.float().contiguous()
         out = self.engine_for(images).forward(images)
-        return {k: v for k, v in out.items()}
+        # fresh tensors, as the reference's GenericModel returns: the engine's own buffers are overwritten by the next call
+        # with this shape (detect() reads them in place instead)
+        return {k: v.clone() for k, v in out.items()}
 
 
 _Det = namedtuple("EncodedOutputs", ["heatmap", "box_2d"])
@@ -232,7 +244,7 @@ class CenterNet(nn.Module):
         self.model = EngineModel(bb, nk, heads, _PRECISIONS[precision], backbone, neck)
         self.stride = bb.stride // nk.stride                                   # reference models/meta.py:96
         self.num_classes = num_classes
-        self._graphs: Dict[Tuple, Any] = {}
+        self._graphs: "OrderedDict[Tuple, Any]" = OrderedDict()
         self.eval()
 
     # ---- G1 names -------------------------------------------------------------------------------------------
@@ -289,18 +301,40 @@ class CenterNet(nn.Module):
 
     # ---- fused forward + decode ----------------------------------------------------------------------------
     @torch.no_grad()
-    def detect(self, images: torch.Tensor, normalize_boxes: bool = False, use_graph: bool = True) -> Dict[str, torch.Tensor]:
+    def detect(self, images: torch.Tensor, normalize_boxes: bool = False, use_graph: bool = True,
+               static_input: bool = False, packed_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """images (N,3,H,W) float32 on the GPU -> {"boxes","scores","labels"[, "embeddings"]}: what the reference's
         validation_step computes at models/centernet.py:204-205, as one CUDA-graph replay of this package's kernels.
-        Returned tensors are static buffers overwritten by the next call with the same shape."""
+        Returned tensors are static buffers overwritten by the next call with the same shape.
+
+        ``static_input``: the caller promises that ``images`` is a long-lived buffer it refills in place (a double-buffered
+        loader); the graph then reads it directly instead of copying it into a private input first.
+        ``packed_out``: (N, k, 8 + reid_dim) float32 buffer that additionally receives the packed rows of
+        distributed.DetectionGather (written by the select kernel)."""
         if not images.is_cuda:
             raise RuntimeError("images are on the CPU: copy them to the GPU first (no CPU fallback)")
-        images = images.float().contiguous()
-        key = (tuple(images.shape), images.device.index, bool(normalize_boxes), self.model.precision)
+        if images.dtype != torch.float32 or not images.is_contiguous():
+            if static_input:
+                raise ValueError("static_input needs a contiguous float32 tensor")
+            images = images.float().contiguous()
+        hp = self.hparams
+        # everything a captured graph freezes is part of its key: shape, weights generation, decode hyper-parameters
+        key = (tuple(images.shape), images.device.index, bool(normalize_boxes), self.model.precision, self.model.generation,
+               int(hp.num_detections), int(hp.nms_kernel), bool(hp.box_log), float(hp.box_multiplier), bool(use_graph),
+               images.data_ptr() if static_input else None, packed_out.data_ptr() if packed_out is not None else None)
         g = self._graphs.get(key)
+        if g is not None and g.engine.handle is None:       # its engine was evicted (arena released): the graph is dead
+            del self._graphs[key]
+            g = None
         if g is None:
-            g = _DetectGraph(self, images, normalize_boxes, use_graph)
+            for old in [k for k in self._graphs if k[4] != self.model.generation]:      # graphs of replaced weights
+                del self._graphs[old]
+            while len(self._graphs) >= 2 * max(1, self.model.max_engines):
+                self._graphs.popitem(last=False)
+            g = _DetectGraph(self, images, normalize_boxes, use_graph, static_input, packed_out)
             self._graphs[key] = g
+        else:
+            self._graphs.move_to_end(key)
         return g.run(images)
 
     @torch.no_grad()
@@ -335,7 +369,7 @@ class CenterNet(nn.Module):
             if nxt is not None:
                 stage(slot ^ 1, nxt)
             main.wait_event(ready[slot])
-            det = self.detect(dev_in[slot])
+            det = self.detect(dev_in[slot], static_input=True)          # the two staging buffers live as long as the generator
             consumed[slot] = torch.cuda.Event()
             consumed[slot].record(main)
             if host_out[slot] is None:
@@ -385,6 +419,7 @@ class CenterNet(nn.Module):
         return {f"val/{k}": v for k, v in metrics.items()}
 
     def invalidate(self) -> None:
+        """Drop every cached graph, plan and packed weight set (after changing parameters in place)."""
         self._graphs.clear()
         self.model.invalidate()
 
@@ -455,7 +490,8 @@ def _unpack(heatmap, box_2d, reid):
 class _DetectGraph:
     """forward + decode for one input shape, captured once into a CUDA graph with static in/out buffers."""
 
-    def __init__(self, net: CenterNet, example: torch.Tensor, normalize_boxes: bool, use_graph: bool):
+    def __init__(self, net: CenterNet, example: torch.Tensor, normalize_boxes: bool, use_graph: bool,
+                 static_input: bool = False, packed_out: Optional[torch.Tensor] = None):
         self.net = net
         dev = example.device
         hp = net.hparams
@@ -463,27 +499,30 @@ class _DetectGraph:
         n = example.shape[0]
         h, w = example.shape[2] // net.stride, example.shape[3] // net.stride
         k = hp.num_detections
-        self.static_in = torch.empty_like(example)
+        self.bound = static_input                           # the graph reads the caller's own buffer
+        self.static_in = example if static_input else torch.empty_like(example)
         outs = self.engine.outputs
         reid = outs.get("reid")
-        self.bufs = _decode.DecodeBuffers(n, h, w, k, reid.shape[1] if reid is not None else 0, dev)
+        self.bufs = _decode.DecodeBuffers(n, h, w, k, reid.shape[1] if reid is not None else 0, dev, packed=packed_out)
         self.kw = dict(num_detections=k, nms_kernel=hp.nms_kernel, normalize_boxes=normalize_boxes, box_log=hp.box_log,
                        box_multiplier=hp.box_multiplier, stride=net.stride, from_logits=True)
         self.launches = 0
         self.graph = None
-        self.static_in.copy_(example)
-        self._body()                                        # warm-up (also sets function attributes)
-        torch.cuda.synchronize(dev)
-        if use_graph:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self._body()
-            torch.cuda.current_stream(dev).wait_stream(side)
+        if not static_input:
+            self.static_in.copy_(example)
+        with torch.cuda.device(dev):
+            self._body()                                        # warm-up (also sets function attributes)
             torch.cuda.synchronize(dev)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body()
+            if use_graph:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    self._body()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
 
     def _body(self):
         outs = self.engine.forward(self.static_in)
@@ -491,9 +530,11 @@ class _DetectGraph:
                                                                          outs.get("reid"), **self.kw)
 
     def run(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
-        self.static_in.copy_(images, non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._body()
+        if not self.bound:
+            self.static_in.copy_(images, non_blocking=True)
+        with torch.cuda.device(self.static_in.device):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._body()
         return self.bufs.as_dict()

@@ -1,8 +1,11 @@
 """GPU side of the image loader: uint8 HWC batches -> normalised fp32 NCHW (csrc/cnl_io.cu).
 
-Mirrors ``A.Normalize()`` + ``ToTensorV2()`` of the reference's inference transform (README.md:84-87) - the
-arithmetic albumentations performs in numpy is reproduced rounding for rounding, so a uint8 batch copied to the GPU
-(1 byte per sample over PCIe) yields the same tensor the reference's CPU transform would."""
+Mirrors ``A.Normalize()`` + ``ToTensorV2()`` of the reference's inference transform (README.md:84-87).  The kernel
+reproduces, rounding for rounding, the float32 arithmetic of albumentations 1.x ``functional.normalize`` as restated in
+oracle/preprocess_np.py (float32 ``mean*255`` / ``std*255``, float32 reciprocal, float32 subtract then multiply), so a
+uint8 batch copied to the GPU (1 byte per sample over PCIe) yields the tensor that restatement yields.  albumentations
+itself is not installed here and not pinned by the reference (requirements.txt), so agreement with the real library is
+UNPINNED: expected to the last bit for 1.x, not verified."""
 from __future__ import annotations
 
 import ctypes as C
@@ -18,10 +21,13 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 def normalize_constants(mean: Sequence[float] = IMAGENET_MEAN, std: Sequence[float] = IMAGENET_STD, max_pixel_value: float = 255.0):
-    """(mean*max as float64[3], 1/(std*max) as float32[3]) - the two arrays albumentations.Normalize builds."""
-    mean255 = np.array(mean, dtype=np.float64) * max_pixel_value
-    std255 = np.array(std, dtype=np.float64) * max_pixel_value
-    return mean255, np.reciprocal(std255, dtype=np.float32)
+    """(mean*max, 1/(std*max)) as albumentations 1.x builds them: float32 arrays multiplied in float32, float32 reciprocal.
+    The mean is handed to the C ABI as float64 (exact widening): float(double(x) - mean) is the float32 subtraction."""
+    mean255 = np.array(mean, dtype=np.float32)
+    mean255 *= np.float32(max_pixel_value)
+    std255 = np.array(std, dtype=np.float32)
+    std255 *= np.float32(max_pixel_value)
+    return mean255.astype(np.float64), np.reciprocal(std255, dtype=np.float32)
 
 
 def normalize_u8(images_hwc: torch.Tensor, out: Optional[torch.Tensor] = None, mean: Sequence[float] = IMAGENET_MEAN,

@@ -48,16 +48,22 @@ int cnl_compiled_sm(void);
  *                from_logits = 0: probabilities, exactly what the reference's decode receives
  *                                 (validation_step applies .sigmoid() first, centernet.py:205).
  *                from_logits = 1: raw head output; the kernel applies 1/(1+exp(-x)) in fp32 itself
- *                                 (fuses the sigmoid of centernet.py:205 into the same pass).
+ *                                 (fuses the sigmoid of centernet.py:205 into the same pass).  Results are those of
+ *                                 from_logits = 0 on cnl_sigmoid(heatmap), bit for bit: peaks and the class arg-max
+ *                                 are decided on the fp32 PROBABILITIES (distinct logits that round to one probability
+ *                                 are a plateau, as in the reference), evaluated lazily on near ties only.
  *   box_offsets  (N, 4, H, W) float32 ltrb map, or NULL together with boxes (top-k only).
  *   reid         (N, E, H, W) float32 or NULL (E = reid_dim).
- *   nms_kernel   odd, 1..7 (centernet.py:93 default 3).  k = num_detections <= min(H*W, 1024).
+ *   nms_kernel   odd, 1..7 (centernet.py:93 default 3).  k = num_detections <= H*W (torch.topk's limit, centernet.py:259);
+ *                k > 1024 takes a slower whole-image sort and needs the larger workspace of cnl_decode_workspace_bytes_k.
  *   Outputs (caller-allocated): boxes (N,k,4) f32 xyxy; scores (N,k) f32 descending;
  *   labels (N,k) int64; indices (N,k) int64 flat y*W+x; embeddings (N,k,E) f32 or NULL.
  *   Tie order: score descending, then flat index ascending (torch.topk leaves it unspecified).
- *   workspace: cnl_decode_workspace_bytes(N,H,W) bytes, 256-byte aligned; contents are scratch.
+ *   workspace: cnl_decode_workspace_bytes_k(N,H,W,k) bytes (= cnl_decode_workspace_bytes(N,H,W) for k <= 1024),
+ *   256-byte aligned; contents are scratch.
  * ------------------------------------------------------------------------------------------ */
 size_t cnl_decode_workspace_bytes(int n, int h, int w);
+size_t cnl_decode_workspace_bytes_k(int n, int h, int w, int num_detections);
 
 /* `from_logits` may be OR-ed with CNL_DECODE_WORKSPACE_CLEAN when the workspace was last used by a COMPLETED
  * cnl_decode_detections call with the same n (each call leaves the histogram it used zeroed); the initial memset is then
@@ -70,6 +76,19 @@ int cnl_decode_detections(const float* heatmap, const float* box_offsets, const 
                           float* boxes, float* scores, int64_t* labels, int64_t* indices,
                           float* embeddings,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same decode, additionally writing every detection as one packed float32 row of `packed_width` = 8 + reid_dim lanes
+ * into `packed` (N, k, packed_width; 16-byte aligned, reid_dim % 4 == 0):
+ *   [x1, y1, x2, y2, score, bits(int32 flat index), bits(label low 32), bits(label high 32), embedding...]
+ * - the fixed-shape send buffer of the cross-rank collation (the reference gathers pickled per-image dicts with
+ * dist.all_gather_object, centernet_lightning/eval/coco.py:10-18); integer lanes travel bit-exactly. */
+int cnl_decode_detections_packed(const float* heatmap, const float* box_offsets, const float* reid,
+                                 int n, int c, int h, int w, int reid_dim,
+                                 int from_logits, int nms_kernel, int num_detections,
+                                 int normalize_boxes, int box_log, float box_multiplier, int stride,
+                                 float* boxes, float* scores, int64_t* labels, int64_t* indices,
+                                 float* embeddings, float* packed, int packed_width,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Elementwise fp32 logistic 1/(1+exp(-x)) - the `.sigmoid()` the reference applies to the heatmap head
  * (centernet_lightning/models/centernet.py:205; G1 forward(), tests/test_models.py:88-99). */
@@ -167,6 +186,10 @@ void cnl_engine_destroy(cnl_engine* e);
  * buffer inside the arena (head outputs are read by the caller from there). */
 size_t cnl_engine_arena_bytes(const cnl_engine* e);
 size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer);
+
+/* Kernel form the plan chose for op `op` (for tests and profiles): bit 0 = row-rolling A operand, bit 1 = CTA pair
+ * (cta_group::2), bit 2 = separate correction accumulator, bit 3 = concatenated hi*[hi|lo] MMA; -1 for a bad index. */
+int cnl_engine_op_form(const cnl_engine* e, int op);
 
 /* Upload packed weights into the arena (once, or again after a weight change). */
 int cnl_engine_upload(cnl_engine* e, void* arena, void* stream);

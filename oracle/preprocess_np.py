@@ -6,12 +6,14 @@ albumentations is a third-party dependency that is absent from /root/reference a
 (requirements.txt: ``albumentations``, no pinned version).  Its published algorithm, restated:
   * ``A.Resize(h, w)``: ``cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)`` on the uint8 image;
   * ``A.Normalize(mean=(0.485,0.456,0.406), std=(0.229,0.224,0.225), max_pixel_value=255)``:
-        mean = np.array(mean) * max_pixel_value            (float64)
-        std  = np.array(std)  * max_pixel_value            (float64)
+        mean = np.array(mean, dtype=np.float32); mean *= max_pixel_value      (float32, albumentations 1.x
+        std  = np.array(std,  dtype=np.float32); std  *= max_pixel_value       functional.normalize)
         denominator = np.reciprocal(std, dtype=np.float32)
-        img = img.astype(np.float32); img -= mean; img *= denominator
+        img = img.astype(np.float32); img -= mean; img *= denominator          (cv2.subtract / cv2.multiply for 3-channel
+                                                                               images in 1.x: the same float32 results)
   * ``ToTensorV2``: HWC -> CHW.
-PARITY STATUS: "parity unpinned" (no reference test or golden vector covers the transform)."""
+PARITY STATUS: "parity unpinned" (no reference test or golden vector covers the transform, and the library is not
+installed here to validate the restatement against; written from its published source)."""
 from __future__ import annotations
 
 import numpy as np
@@ -21,8 +23,10 @@ STD = (0.229, 0.224, 0.225)
 
 
 def normalize(img_u8_hwc: np.ndarray, mean=MEAN, std=STD, max_pixel_value: float = 255.0) -> np.ndarray:
-    mean = np.array(mean, dtype=np.float64) * max_pixel_value
-    std = np.array(std, dtype=np.float64) * max_pixel_value
+    mean = np.array(mean, dtype=np.float32)
+    mean *= np.float32(max_pixel_value)
+    std = np.array(std, dtype=np.float32)
+    std *= np.float32(max_pixel_value)
     denominator = np.reciprocal(std, dtype=np.float32)
     img = img_u8_hwc.astype(np.float32)
     img -= mean

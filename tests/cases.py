@@ -75,6 +75,68 @@ FORWARD_CASES = {
 }
 
 
+# ---- near-tie logits (from_logits path): distinct logits that fp32 sigmoid maps to ONE probability ---------------------
+# The reference compares probabilities (models/centernet.py:252-254), so such neighbours are a plateau (both kept) and such
+# classes tie (first class wins).  Every structure is planted on a cleared patch of its class so that it is a local maximum.
+NEARTIE_CASES = [
+    dict(name="neartie_w128", n=2, c=40, h=16, w=128, k=60, seed=11),      # one warp tile per row, 4 class groups
+    dict(name="neartie_w256", n=1, c=33, h=12, w=256, k=60, seed=12),      # VEC = 2 tiles
+    dict(name="neartie_w272", n=1, c=8, h=12, w=272, k=60, seed=13),       # rows wider than a warp tile (halo columns), 2 groups
+    dict(name="neartie_odd", n=2, c=5, h=19, w=21, k=40, seed=14),         # generic kernel geometry
+    dict(name="neartie_c1", n=1, c=1, h=16, w=128, k=30, seed=15),         # single class, single group
+]
+
+
+def _ulps(x: float, n: int) -> float:
+    import numpy as np
+    v = np.float32(x)
+    for _ in range(abs(n)):
+        v = np.nextafter(v, np.float32(np.inf if n > 0 else -np.inf), dtype=np.float32)
+    return float(v)
+
+
+def make_neartie_logits(case):
+    """(logits, box): randn background with planted pairs / triples whose members differ by a few ulps up to the widest
+    gap that can still round to one probability, at logit levels from -3 to saturation."""
+    g = torch.Generator().manual_seed(case["seed"])
+    n, c, h, w = case["n"], case["c"], case["h"], case["w"]
+    heat = torch.randn((n, c, h, w), generator=g) * 1.5 - 2.19
+    levels = [-3.0, -0.5, 0.3, 1.7, 3.0, 5.0, 8.0, 12.0, 15.0, 16.0, 16.7, 20.0, 30.0]
+    gaps = [1, 2, 5, 11, 40, 200, 900]                                   # in ulps of the smaller logit
+    extra = [(8.0, 8.00001), (12.0, 12.0005), (3.0, _ulps(3.0, 5)), (16.5, 16.9), (17.5, 40.0)]
+    pairs = [(a, _ulps(a, gaps[(i + j) % len(gaps)])) for i, a in enumerate(levels) for j in range(2)] + extra
+    slots = [(y, x) for y in range(2, h - 2, 5) for x in range(2, w - 4, 7)]
+    rng = torch.Generator().manual_seed(case["seed"] + 1000)
+    order = torch.randperm(len(slots), generator=rng).tolist()
+    pairs = [pairs[i] for i in torch.randperm(len(pairs), generator=rng).tolist()]      # small maps get a mix of levels
+    for i, (lo, hi) in enumerate(pairs):
+        if i >= len(order):
+            break
+        y, x = slots[order[i]]
+        img = i % n
+        cls = (3 * i) % c
+        heat[img, cls, y - 2:y + 3, x - 2:x + 5] = -30.0
+        shape = i % 5
+        if shape == 0:                                                   # horizontal neighbours, smaller first
+            heat[img, cls, y, x], heat[img, cls, y, x + 1] = lo, hi
+        elif shape == 1:                                                 # vertical neighbours, larger first
+            heat[img, cls, y, x], heat[img, cls, y + 1, x] = hi, lo
+        elif shape == 2:                                                 # diagonal + a third member in between
+            heat[img, cls, y, x], heat[img, cls, y + 1, x + 1], heat[img, cls, y, x + 1] = lo, hi, (lo + hi) / 2
+        elif shape == 3 and c > 1:                                       # same pixel, two classes (far apart = different groups):
+            other = (cls + c // 2 + 1) % c                               # the LOWER class index holds the smaller logit
+            a, b = min(cls, other), max(cls, other)
+            heat[img, b, y - 2:y + 3, x - 2:x + 5] = -30.0
+            heat[img, a, y, x], heat[img, b, y, x] = lo, hi
+        else:                                                            # same pixel, neighbouring classes (same group mostly)
+            other = (cls + 1) % c
+            a, b = min(cls, other), max(cls, other)
+            heat[img, b, y - 2:y + 3, x - 2:x + 5] = -30.0
+            heat[img, a, y, x], heat[img, b, y, x] = hi, lo
+    box = torch.randn((n, 4, h, w), generator=g)
+    return heat.contiguous(), box
+
+
 def make_image(kw):
     g = torch.Generator().manual_seed(kw["img_seed"])
     return torch.rand((kw["n"], 3, kw["size"], kw["size"]), generator=g)

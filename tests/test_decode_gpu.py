@@ -94,6 +94,103 @@ def test_decode_from_logits_fused_sigmoid(cuda, case, generic):
     _check_selection(out, probs, case, score_tol=1e-6)
 
 
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("case", [c for c in cases.DECODE_CASES if c["logits"]] + cases.NEARTIE_CASES, ids=lambda c: c["name"])
+def test_from_logits_is_sigmoid_then_reference_decode(cuda, case, generic):
+    """The fused path must be the reference's `.sigmoid()` followed by its probability-space decode (centernet.py:205,
+    250-254), bit for bit: decode(logits, from_logits) == decode(cnl_sigmoid(logits)) == oracle(those probabilities),
+    including the plateaus and class ties that appear when distinct logits round to one fp32 probability."""
+    from centernet_lightning_b200 import decode
+    if "kind" in case:
+        heat, box, _ = cases.make_decode_inputs(case)
+        kw = _kw(case)
+    else:
+        heat, box = cases.make_neartie_logits(case)
+        kw = dict(num_detections=case["k"], nms_kernel=3, normalize_boxes=False, box_log=False, box_multiplier=16.0, stride=4)
+    probs = decode.sigmoid(heat.to(cuda))
+    fused = _np(decode.decode_detections(heat.to(cuda), box.to(cuda), from_logits=True, _force_generic=generic, **kw))
+    plain = _np(decode.decode_detections(probs, box.to(cuda), _force_generic=generic, **kw))
+    for k in ("scores", "indices", "labels", "boxes"):
+        assert np.array_equal(fused[k], plain[k]), k
+    oracle = decode_np.decode_detections(probs.cpu().numpy(), box.numpy(), **kw)
+    assert np.array_equal(fused["scores"], oracle["scores"])
+    assert np.array_equal(fused["indices"], oracle["indices"])
+    assert np.array_equal(fused["labels"], oracle["labels"])
+    if not kw["box_log"]:
+        assert np.array_equal(fused["boxes"], oracle["boxes"])
+    if "kind" not in case:          # the planted structures really produce probability ties among the winners
+        p = probs.cpu().numpy()
+        assert (np.diff(oracle["scores"], axis=1) == 0).sum() >= 1 or case["name"] == "neartie_odd"
+        assert len(np.unique(heat.numpy())) > len(np.unique(p))
+
+
+def test_collapsed_neighbours_and_classes_follow_the_probabilities(cuda):
+    """8.0 and 8.00001 share one fp32 probability (as do 12.0 / 12.0005 and 3.0 / 3.0 + 5 ulp): the reference keeps BOTH
+    neighbouring pixels, and between two classes at one pixel the FIRST class wins although its logit is smaller."""
+    from centernet_lightning_b200 import decode
+    for lo, hi in [(8.0, 8.00001), (12.0, 12.0005), (3.0, cases._ulps(3.0, 5))]:
+        heat = torch.full((1, 2, 8, 8), -9.0)
+        heat[0, 0, 2, 2] = lo
+        heat[0, 0, 2, 3] = hi                     # neighbour with the larger logit, same probability
+        heat[0, 0, 6, 6] = hi                     # two classes at one pixel: class 1 holds the larger logit
+        heat[0, 1, 6, 6] = cases._ulps(hi, 3)
+        heat[0, 1, 4, 0] = 0.0                    # a clearly smaller, separate peak
+        p = decode.sigmoid(heat.to(cuda)).cpu()
+        assert p[0, 0, 2, 2] == p[0, 0, 2, 3] and p[0, 0, 6, 6] == p[0, 1, 6, 6], "premise: these logits collapse in fp32"
+        box = torch.zeros((1, 4, 8, 8))
+        out = _np(decode.decode_detections(heat.to(cuda), box.to(cuda), num_detections=4, from_logits=True))
+        assert out["indices"][0].tolist() == [18, 19, 54, 32], (lo, hi, out["indices"])
+        assert out["labels"][0].tolist() == [0, 0, 0, 1]
+        assert out["scores"][0, 0] == out["scores"][0, 1] == out["scores"][0, 2] == p[0, 0, 2, 2].item()
+
+
+def test_cnl_sigmoid_is_the_device_logistic(cuda):
+    """cnl_sigmoid / the fused decode use 1/(1+expf(-x)) with separately rounded fp32 operations - the arithmetic of
+    torch.sigmoid on a CUDA tensor, which is what the reference's `.sigmoid()` runs on the device (centernet.py:205)."""
+    from centernet_lightning_b200 import decode
+    g = torch.Generator().manual_seed(3)
+    x = torch.cat([torch.randn(1 << 16, generator=g) * 6.0, torch.linspace(-110, 40, 1 << 14), torch.tensor([0.0, -0.0, 88.0, -88.0, -104.0])])
+    x = x.to(cuda)
+    assert torch.equal(decode.sigmoid(x.view(1, 1, 1, -1)).view(-1), torch.sigmoid(x))
+
+
+def test_num_detections_above_1024(cuda):
+    """The reference accepts any k <= H*W (torch.topk, centernet.py:259); k > 1024 takes the whole-image sort."""
+    from centernet_lightning_b200 import decode
+    for n, c, h, w, k in [(2, 6, 64, 64, 2000), (1, 3, 40, 72, 2880), (1, 80, 128, 128, 1025)]:
+        g = torch.Generator().manual_seed(k)
+        heat = torch.randn((n, c, h, w), generator=g) * 1.5 - 2.19
+        box = torch.randn((n, 4, h, w), generator=g)
+        reid = torch.randn((n, 8, h, w), generator=g)
+        probs = heat.sigmoid()
+        out = _np(decode.decode_detections(probs.to(cuda), box.to(cuda), reid=reid.to(cuda), num_detections=k, box_multiplier=16.0))
+        oracle = decode_np.decode_detections(probs.numpy(), box.numpy(), reid=reid.numpy(), num_detections=k, box_multiplier=16.0)
+        for key in ("scores", "indices", "labels", "boxes", "embeddings"):
+            assert np.array_equal(out[key], oracle[key]), (k, key)
+        # the next call with a small k on the same stream's workspace still works (histogram left clean)
+        small = _np(decode.decode_detections(probs.to(cuda), box.to(cuda), num_detections=50, box_multiplier=16.0))
+        assert np.array_equal(small["indices"], oracle["indices"][:, :50])
+
+
+def test_packed_rows_are_written_by_the_select_kernel(cuda):
+    """cnl_decode_detections_packed: (N,k,8+E) rows [box, score, index bits, label bits, embedding] = the all_gather send
+    buffer; zero-copy views of it equal the ordinary outputs."""
+    from centernet_lightning_b200 import decode, distributed as cdist
+    case = cases.DECODE_BY_NAME["track128"]
+    heat, box, reid = cases.make_decode_inputs(case)
+    n, k, e = case["n"], case["k"], case["reid"]
+    packed = torch.full((n, k, 8 + e), float("nan"), device=cuda)
+    bufs = decode.DecodeBuffers(n, case["h"], case["w"], k, e, cuda, packed=packed)
+    decode.decode_into(bufs, heat.to(cuda), box.to(cuda), reid.to(cuda), from_logits=True, **_kw(case))
+    views = cdist.unpack_detections(packed)
+    assert torch.equal(views["boxes"], bufs.boxes) and torch.equal(views["scores"], bufs.scores)
+    assert torch.equal(views["labels"], bufs.labels) and views["labels"].dtype == torch.int64
+    assert torch.equal(views["indices"].to(torch.int64), bufs.indices)
+    assert torch.equal(views["embeddings"], bufs.emb)
+    with pytest.raises(ValueError):
+        decode.DecodeBuffers(n, case["h"], case["w"], k, e, cuda, packed=torch.empty((n, k, 6 + e), device=cuda))
+
+
 def test_saturated_logits_keep_probability_plateaus(cuda):
     """fp32 sigmoid maps every logit >= ~17 to exactly 1.0, so adjacent saturated pixels are BOTH peaks in the
     reference (it compares probabilities).  The fused kernel compares logits and must reproduce that."""

@@ -30,6 +30,52 @@ def _build(kw, precision="split"):
     return spec, net
 
 
+BOX_TOL = 64 * TOL        # boxes = (centre -/+ raw * box_multiplier 16) * stride 4: a raw-map error e moves a box edge by 64 e pixels
+
+
+def _assert_detections_agree(det, ref_maps, k=100, mult=16.0, min_robust=50):
+    """End-to-end agreement of detect() with the oracle pipeline run on the ORACLE's maps (forward + decode both differ).
+
+    The engine's maps are within TOL of the oracle's, so a detection can legitimately change only where the decision was
+    closer than that.  An oracle detection is ROBUST when (a) its score clears the k-th score by more than 2 TOL, (b) it
+    beats every neighbour of its 3x3 window in its class by more than 2 TOL (the peak cannot move) and (c) it beats every
+    other class's kept value at that pixel by more than 2 TOL (the label cannot flip).  Every robust detection must be
+    returned by detect() at the same pixel with the same label, its score within TOL and its box within BOX_TOL pixels."""
+    probs = decode_np.sigmoid_f32(ref_maps["heatmap"])
+    oracle = decode_np.decode_detections(probs, ref_maps["box_2d"], num_detections=k, box_multiplier=mult)
+    n, c, h, w = probs.shape
+    pad = np.full((n, c, h + 2, w + 2), -np.inf, dtype=np.float32)
+    pad[:, :, 1:-1, 1:-1] = probs
+    kept = probs * (decode_np._maxpool_same(probs, 3) == probs)
+    got_boxes = det["boxes"].cpu().numpy()
+    got_scores = det["scores"].cpu().numpy()
+    got_labels = det["labels"].cpu().numpy()
+    got_idx = np.round((got_boxes[..., 0] + got_boxes[..., 2]) / 8 - 0.5).astype(int)      # not used for matching (boxes may be clamped)
+    total_robust = 0
+    for i in range(n):
+        kth = oracle["scores"][i, -1]
+        # detect() does not return indices: recover each returned detection's pixel through the engine-independent oracle
+        # candidate map - match by (label, score within TOL, box within BOX_TOL)
+        for j in range(k):
+            s, idx, lab = oracle["scores"][i, j], int(oracle["indices"][i, j]), int(oracle["labels"][i, j])
+            y, x = divmod(idx, w)
+            if s <= kth + 2 * TOL:
+                continue
+            win = pad[i, lab, y:y + 3, x:x + 3].copy()
+            win[1, 1] = -np.inf
+            if s - win.max() <= 2 * TOL:
+                continue
+            others = np.delete(kept[i, :, y, x], lab)
+            if others.size and s - others.max() <= 2 * TOL:
+                continue
+            total_robust += 1
+            cand = np.where((got_labels[i] == lab) & (np.abs(got_scores[i] - s) <= TOL))[0]
+            ok = [q for q in cand if np.abs(got_boxes[i, q] - oracle["boxes"][i, j]).max() <= BOX_TOL]
+            assert ok, f"image {i}: oracle detection {j} (pixel {idx}, label {lab}, score {s:.6f}) is missing from detect()"
+    assert total_robust >= min_robust * n, f"only {total_robust} robust detections: the comparison would be vacuous"
+    return total_robust
+
+
 def test_conv_probes_subset(cuda):
     """Single fused-conv launches vs torch fp64 (full list: tools/conv_probe.py; log in profiles/)."""
     import sys
@@ -101,12 +147,8 @@ def test_forward_256_matches_oracle_and_decode_agrees(cuda):
     oracle = decode_np.decode_detections(probs, ref["box_2d"].numpy(), num_detections=100, box_multiplier=16.0)
     s = det["scores"].cpu().numpy()
     np.testing.assert_allclose(s, oracle["scores"], rtol=0, atol=TOL)
-    # index/label agreement: compare as sets over detections whose score gap to the k-th is above the tolerance
-    for i in range(2):
-        kth = oracle["scores"][i, -1]
-        keep = oracle["scores"][i] > kth + 2 * TOL
-        got = set(zip(det["labels"][i].cpu().tolist(), np.round(det["boxes"][i].cpu().numpy()[:, 0] / 4).astype(int).tolist()))
-        assert keep.sum() > 50
+    # end-to-end: every decision that was not closer than the tolerance comes out the same, boxes within 64 TOL pixels
+    _assert_detections_agree(det, {k: v.numpy() for k, v in ref.items()})
     boxes = det["boxes"].cpu().numpy()
     assert np.isfinite(boxes).all() and boxes.shape == (2, 100, 4)
     # detect() is deterministic and graph replay equals eager launch
@@ -114,6 +156,79 @@ def test_forward_256_matches_oracle_and_decode_agrees(cuda):
     det3 = net.detect(x.to(cuda), use_graph=True)
     for k in det2:
         assert torch.equal(det2[k], det3[k])
+
+
+def test_bench_configuration_512_batch8(cuda):
+    """The benchmarked configuration itself (BASELINE configs[1]: ResNet-34 + FPN, 80 classes, 3x512x512, k=100) at batch 8:
+    the kernel forms are chosen by the PRODUCTION thresholds - CTA pairs (cta_group::2) for the 128x128 tower / FPN convs
+    (8 x 128 = 1024 tiles), the row-rolling form for layer1 - and the result is held to the same bars: raw maps within
+    1e-3 of the CPU fp32 oracle, detections in end-to-end agreement."""
+    kw = dict(model=dict(num_classes=80), seed=7, n=8, size=512, img_seed=17)
+    spec, net = _build(kw)
+    net = net.to(cuda)
+    x = cases.make_image(kw)
+    with torch.no_grad():
+        ref = spec(x)
+    out = net.model(x.to(cuda))
+    forms = net.model.engine_for(x.to(cuda)).kernel_forms()
+    assert forms["heads.heatmap.block_2"] == "pair" and forms["neck.output.0"] == "pair", forms
+    assert forms["backbone.layer1.0.conv1"] == "rows", forms
+    for k in ref:
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=0, atol=TOL, err_msg=k)
+    det = net.detect(x.to(cuda))
+    _assert_detections_agree(det, {k: v.numpy() for k, v in ref.items()})
+
+
+def test_detect_follows_hparams_and_reloaded_weights(cuda):
+    """The captured graph is keyed by everything it freezes: changing num_detections between two calls on one input shape,
+    or loading new weights, must not replay a stale graph (round-1 advisor findings)."""
+    kw = dict(model=dict(num_classes=80), seed=0, n=1, size=64, img_seed=3)
+    spec, net = _build(kw)
+    net = net.to(cuda)
+    x = cases.make_image(kw).to(cuda)
+    net.hparams.num_detections = 20
+    d20 = {k: v.clone() for k, v in net.detect(x).items()}
+    net.hparams.num_detections = 50
+    d50 = {k: v.clone() for k, v in net.detect(x).items()}
+    assert tuple(d20["boxes"].shape) == (1, 20, 4) and tuple(d50["boxes"].shape) == (1, 50, 4)
+    assert torch.equal(d50["scores"][:, :20], d20["scores"])
+    # reload other weights: same shape, the detections must be those of the new weights
+    spec2 = spec_model.synth_init(spec_model.build_spec_model(80), seed=9)
+    net.load_state_dict({f"model.{k}": v for k, v in spec2.state_dict().items()})
+    new = {k: v.clone() for k, v in net.detect(x).items()}
+    assert not torch.equal(new["scores"], d50["scores"])
+    fresh = _build(dict(kw, seed=9))[1].to(cuda)
+    fresh.hparams.num_detections = 50
+    ref = fresh.detect(x)
+    for k in new:
+        assert torch.equal(new[k], ref[k]), k
+    net.model.load_state_dict(spec.state_dict())               # reload through the inner module as the tests do
+    back = net.detect(x)
+    assert torch.equal(back["scores"], d50["scores"])
+    # eager (use_graph=False) path after a reload works too
+    assert torch.equal(net.detect(x, use_graph=False)["scores"], d50["scores"])
+
+
+def test_model_outputs_are_fresh_and_caches_are_bounded(cuda):
+    """model(x) returns tensors the next call does not overwrite (the reference's GenericModel does); engines are evicted
+    least-recently-used beyond max_engines, and a graph whose engine was evicted is rebuilt, not replayed."""
+    kw = dict(model=dict(num_classes=80), seed=0, n=1, size=64, img_seed=3)
+    _, net = _build(kw)
+    net = net.to(cuda)
+    x1 = cases.make_image(kw).to(cuda)
+    x2 = cases.make_image(dict(kw, img_seed=4)).to(cuda)
+    o1 = net.model(x1)
+    keep = o1["heatmap"].clone()
+    o2 = net.model(x2)
+    assert torch.equal(o1["heatmap"], keep) and not torch.equal(o2["heatmap"], keep)
+    net.model.max_engines = 2
+    first = {k: v.clone() for k, v in net.detect(x1).items()}
+    for size in (96, 128, 160):
+        net.detect(torch.rand((1, 3, size, size), device=cuda))
+    assert len(net.model._engines) <= 2
+    again = net.detect(x1)
+    for k in first:
+        assert torch.equal(first[k], again[k]), k
 
 
 def test_config1_simple_neck_512_matches_oracle(cuda):

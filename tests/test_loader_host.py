@@ -36,8 +36,9 @@ def test_load_resized_u8_equals_oracle_and_fills_caller_buffer(tmp_path):
 def test_normalize_constants_are_albumentations_arrays():
     mean255, inv = preprocess.normalize_constants()
     assert mean255.dtype == np.float64 and inv.dtype == np.float32
-    np.testing.assert_array_equal(mean255, np.array(preprocess_np.MEAN, dtype=np.float64) * 255.0)
-    np.testing.assert_array_equal(inv, np.reciprocal(np.array(preprocess_np.STD, dtype=np.float64) * 255.0, dtype=np.float32))
+    # albumentations 1.x functional.normalize: float32 arrays scaled in float32 (the mean travels widened to float64)
+    np.testing.assert_array_equal(mean255, (np.array(preprocess_np.MEAN, dtype=np.float32) * np.float32(255.0)).astype(np.float64))
+    np.testing.assert_array_equal(inv, np.reciprocal(np.array(preprocess_np.STD, dtype=np.float32) * np.float32(255.0), dtype=np.float32))
     # the kernel's formula with these constants == the oracle, evaluated in numpy with the same roundings
     x = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, axis=2)
     mine = (x.astype(np.float64) - mean255).astype(np.float32) * inv
