@@ -32,16 +32,19 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu -> libcnl_b200.so.  Returns the library path."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), lib_out: str = LIB) -> str:
+    """Compile csrc/*.cu -> libcnl_b200.so.  Returns the library path.  `defines` / `lib_out` build an A/B variant of the same
+    library next to it (loaded through CNL_LIB for timing experiments; never a fallback)."""
+    variant = lib_out != LIB
+    if not force and not variant and not _stale():
         return LIB
     nvcc = _nvcc()
     objs = []
     procs = []
+    tag = "" if not variant else "." + os.path.splitext(os.path.basename(lib_out))[0]
     for s in SOURCES:
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        obj = os.path.join(CSRC, s.replace(".cu", tag + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
@@ -53,11 +56,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
         if verbose:
             print(out, file=sys.stderr)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_out, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":

@@ -19,6 +19,10 @@
 #include <type_traits>
 #include "cnl_common.h"
 
+#ifndef CNL_NEARTIE_MODE
+#define CNL_NEARTIE_MODE 2
+#endif
+
 namespace cnl {
 
 static thread_local char g_err[512] = "";
@@ -53,10 +57,16 @@ __device__ __forceinline__ float sigmoid32(float x) { return __fdiv_rn(1.0f, __f
 // slope >= 0.25 e^-m) that is m - x <= 1.43e-6 e^m, for m < 0 (ulp <= 2^-23 p, slope >= p/2) m - x <= 1.43e-6.
 // Returned: 2^-18 * 2^ceil(max(m,0) * log2 e) (>= 2.6x the bound).  Saturated (>= 16.5: p is 1 - 2^-24 or 1) and
 // underflowing (< -80: p is denormal or 0, absolute spacing) logits have no useful bound: +inf, always take the exact test.
+// collapse_exp: the exponent e of that power of two (thr = 2^e), or kNoBound.
+constexpr int kNoBound = 1 << 20;
+__device__ __forceinline__ int collapse_exp(float m) {
+  if (!(m > -80.0f && m < 16.5f)) return kNoBound;            // also catches NaN
+  return (int)ceilf(fmaxf(m, 0.0f) * 1.4426950f) - 18;       // -18 .. 6
+}
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }
 __device__ __forceinline__ float collapse_thr(float m) {
-  if (!(m > -80.0f && m < 16.5f)) return INFINITY;           // also catches NaN
-  const int e = (int)ceilf(fmaxf(m, 0.0f) * 1.4426950f) - 18;
-  return __int_as_float((127 + e) << 23);
+  const int e = collapse_exp(m);
+  return e == kNoBound ? INFINITY : pow2f(e);
 }
 // exact peak test of the from_logits path for a centre x below its window max m
 __device__ __forceinline__ bool same_probability(float x, float m) { return sigmoid32(x) == sigmoid32(m); }
@@ -169,7 +179,7 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
       }
     };
     load_strip();
-    float thr = 0.0f;
+    int thr_e = 0;                                   // exponent of the near-tie threshold of this lane's strip (kNoBound: none)
     if constexpr (LOGITS && P > 0) {
       // largest logit this lane can see as a window max: its own columns, its neighbour lanes' and the halo columns
       float4 t4 = v[0][0];
@@ -185,11 +195,17 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
           for (int q = 0; q < P; ++q) tmax = fmaxf(tmax, hx[j][q]);
       }
       const float tl = __shfl_sync(0xffffffffu, tmax, (lane + 31) & 31), tr = __shfl_sync(0xffffffffu, tmax, (lane + 1) & 31);
-      thr = collapse_thr(fmaxf(tmax, fmaxf(tl, tr)));
+      thr_e = collapse_exp(fmaxf(tmax, fmaxf(tl, tr)));
     }
     // one walk over the strip's rows; EXACT = false: x == m test (+ smallest non-zero gap), EXACT = true: probability test
     // for the centres that are below their window max by less than thr
+    // near-tie detector of the fast walk.  CNL_NEARTIE_MODE 1: smallest non-zero gap m - x (FSEL + FMNMX on the ALU pipe,
+    // the pipe this kernel loads most); mode 2: FMA-pipe only - g = sat((m - x) / thr) is 0 for a peak, 1 for a clear
+    // non-peak and strictly in between for a near tie, so acc = sum g (1 - g) is non-zero iff the strip holds one
+    // (every term is >= 0: no cancellation; denormal gaps keep g > 0 because thr <= 2^7).
     float gap = INFINITY;
+    float acc = 0.0f;
+    const float inv_thr = (thr_e == kNoBound) ? 0.0f : pow2f(-thr_e);
     auto walk = [&](auto exact_tag, float thr) {
       constexpr bool EXACT = decltype(exact_tag)::value;
 #pragma unroll
@@ -241,7 +257,14 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
             for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[4 * u + j + q]);
             if constexpr (!EXACT) {
               masked_max<LOGITS>(best[i][4 * u + j], ctr[j], m);
-              if constexpr (LOGITS && P > 0) gap = fminf(gap, (ctr[j] == m) ? INFINITY : m - ctr[j]);
+              if constexpr (LOGITS && P > 0) {
+#if CNL_NEARTIE_MODE == 1
+                gap = fminf(gap, (ctr[j] == m) ? INFINITY : m - ctr[j]);
+#elif CNL_NEARTIE_MODE == 2
+                const float gq = __saturatef((m - ctr[j]) * inv_thr);          // NaN (out-of-map centre) saturates to 0
+                acc = fmaf(-gq, gq, acc + gq);
+#endif
+              }
             } else {
               // (an out-of-map centre is -inf: m - ctr = inf or NaN, never below thr)
               if (ctr[j] != m && m - ctr[j] < thr && same_probability(ctr[j], m)) best[i][4 * u + j] = fmaxf(best[i][4 * u + j], ctr[j]);
@@ -252,7 +275,15 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
     };
     walk(std::false_type{}, 0.0f);
     if constexpr (LOGITS && P > 0) {
-      if (__any_sync(0xffffffffu, gap < thr)) {      // near tie somewhere in this warp's strip: rare
+      const float thr = (thr_e == kNoBound) ? INFINITY : pow2f(thr_e);
+#if CNL_NEARTIE_MODE == 1
+      const bool near = gap < thr;
+#elif CNL_NEARTIE_MODE == 2
+      const bool near = (acc > 0.0f) || (thr_e == kNoBound);
+#else
+      const bool near = false;                        // (timing experiments only: round-1 behaviour, not reference-exact)
+#endif
+      if (__any_sync(0xffffffffu, near)) {            // near tie somewhere in this warp's strip: rare
         load_strip();                                // (re-read from L2: the strip's registers were released during the walk)
         walk(std::true_type{}, thr);
       }
@@ -797,7 +828,6 @@ select_gather_kernel(DecodeParams p) {
   const size_t plane = (size_t)HW;
   const float* img = p.heat + (size_t)n * p.C * plane;
   const int sub = tid & 7;
-  const int scan_len = (p.group_classes > 0) ? p.group_classes : p.C;       // classes to re-read per winner (CTA-uniform)
   for (int j0 = 0; j0 < k; j0 += kSelThreads / 8) {
     const int j = j0 + (tid >> 3);
     const bool act = j < k;
@@ -813,10 +843,12 @@ select_gather_kernel(DecodeParams p) {
     // kernel 1 recorded which class group attained the maximum: only those classes are re-read (the C planes of one
     // pixel are 4*H*W bytes apart - same DRAM bank - so every class read costs a row activation)
     int c_lo = 0, c_hi = p.C;
-    if (act) {
+    if (act && p.group_classes > 0) {
       const int gid = have_grp ? (int)s_grp_sorted[j] : (int)p.cgroup[(size_t)n * HW + idx];
-      if (gid != 0xff) { c_lo = gid * p.group_classes; c_hi = min(p.C, c_lo + p.group_classes); }
+      if (gid != 0xff) { c_lo = gid * p.group_classes; c_hi = min(p.C, c_lo + p.group_classes); }    // 0xff: group unknown, scan all
     }
+    // classes to re-read: warp-uniform trip count (the 8 lanes of a winner exchange their results by shuffles)
+    const int scan_len = __reduce_max_sync(0xffffffffu, act ? (c_hi - c_lo) : 0);
     // the winners' box-map values travel with their class values (independent loads, same round trip)
     float braw = 0.f;
     if (p.box != nullptr && act && sub < 4) braw = __ldg(p.box + ((size_t)n * 4 + sub) * plane + idx);
@@ -994,8 +1026,9 @@ int cnl_decode_detections_packed(const float* heatmap, const float* box_offsets,
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: bad shape (%d,%d,%d,%d)", n, c, h, w);
   if (c > 65535) return fail(CNL_ERR_UNSUPPORTED, "cnl_decode_detections: more than 65535 classes");
   if ((long long)h * w > (1ll << 30)) return fail(CNL_ERR_UNSUPPORTED, "cnl_decode_detections: map too large");
-  if (from_logits & ~(1 | CNL_DECODE_WORKSPACE_CLEAN)) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: bad from_logits flags %d", from_logits);
+  if (from_logits & ~(1 | CNL_DECODE_WORKSPACE_CLEAN | CNL_DECODE_PEAKS_ONLY)) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: bad from_logits flags %d", from_logits);
   const bool workspace_clean = (from_logits & CNL_DECODE_WORKSPACE_CLEAN) != 0;
+  const bool peaks_only = (from_logits & CNL_DECODE_PEAKS_ONLY) != 0;
   from_logits &= 1;
   // a negative or even kernel changes the pooled map's size in the reference (F.max_pool2d would not broadcast)
   int force_generic = 0;
@@ -1023,11 +1056,12 @@ int cnl_decode_detections_packed(const float* heatmap, const float* box_offsets,
   const int P = (nms_kernel - 1) / 2;
   // the select kernel zeroes the histogram after reading it, so a workspace that was last used by a completed decode of the
   // same batch size needs no memset (CNL_DECODE_WORKSPACE_CLEAN); a fresh or foreign workspace does
-  if (!workspace_clean) CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
+  if (!workspace_clean && !peaks_only) CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
   uint8_t* cgroup = reinterpret_cast<uint8_t*>(static_cast<char*>(workspace) + hist_bytes(n) + score_bytes(n, h, w));
   const int group_classes = from_logits ? launch_peaks<true>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st)
                                         : launch_peaks<false>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st);
   CNL_CUDA_CHECK(cudaGetLastError());
+  if (peaks_only) return CNL_OK;
 
   DecodeParams p;
   p.cscore = cscore; p.hist = hist; p.box = box_offsets; p.reid = reid;

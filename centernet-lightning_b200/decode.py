@@ -79,13 +79,15 @@ class DecodeBuffers:
 
 def decode_into(bufs: DecodeBuffers, heatmap: torch.Tensor, box_offsets: torch.Tensor, reid: Optional[torch.Tensor], *,
                 num_detections: int, nms_kernel: int, normalize_boxes: bool, box_log: bool, box_multiplier: float,
-                stride: int, from_logits: bool) -> int:
+                stride: int, from_logits: bool, _peaks_only: bool = False) -> int:
     """Allocation-free decode on the current stream (CUDA-graph capturable).  Returns the number of launches."""
     lib = _lib.load()
     n, c, h, w = heatmap.shape
     if (n, h, w, num_detections) != (bufs.n, bufs.h, bufs.w, bufs.k):
         raise ValueError("DecodeBuffers were built for another shape")
     flags = int(bool(from_logits)) | (2 if bufs.clean else 0)           # CNL_DECODE_WORKSPACE_CLEAN
+    if _peaks_only:
+        flags = int(bool(from_logits)) | 4                              # CNL_DECODE_PEAKS_ONLY (profiling: memset + peaks kernel)
     bufs.clean = False
     st = lib.cnl_decode_detections_packed(
         heatmap.data_ptr(), box_offsets.data_ptr(), reid.data_ptr() if reid is not None else None,
@@ -96,7 +98,7 @@ def decode_into(bufs: DecodeBuffers, heatmap: torch.Tensor, box_offsets: torch.T
         bufs.packed.data_ptr() if bufs.packed is not None else None, bufs.packed.shape[-1] if bufs.packed is not None else 0,
         bufs.ws.data_ptr(), bufs.ws.numel(), torch.cuda.current_stream(heatmap.device).cuda_stream)
     _lib.check(st, "cnl_decode_detections")
-    bufs.clean = True
+    bufs.clean = not _peaks_only
     return 2 if flags & 2 else 3            # [memset +] peaks + select
 
 

@@ -69,6 +69,10 @@ size_t cnl_decode_workspace_bytes_k(int n, int h, int w, int num_detections);
  * cnl_decode_detections call with the same n (each call leaves the histogram it used zeroed); the initial memset is then
  * skipped.  Never set it for a fresh workspace. */
 #define CNL_DECODE_WORKSPACE_CLEAN 2
+/* Profiling aid, OR-ed into `from_logits`: launch only the streaming (peaks) kernel and skip the per-image select, so that
+ * the HBM-bound pass can be timed alone with CUDA events.  Outputs are not written and the workspace histogram is left
+ * dirty: the next call on this workspace must not claim CNL_DECODE_WORKSPACE_CLEAN. */
+#define CNL_DECODE_PEAKS_ONLY 4
 int cnl_decode_detections(const float* heatmap, const float* box_offsets, const float* reid,
                           int n, int c, int h, int w, int reid_dim,
                           int from_logits, int nms_kernel, int num_detections,
