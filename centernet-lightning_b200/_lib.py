@@ -16,7 +16,7 @@ EXPORTS = (
     "cnl_decode_workspace_bytes", "cnl_decode_workspace_bytes_k", "cnl_decode_detections", "cnl_decode_detections_packed", "cnl_gather_boxes", "cnl_sigmoid", "cnl_boxes_xyxy_to_xywh",
     "cnl_normalize_images_u8", "cnl_track_workspace_bytes", "cnl_track_cost_matrices",
     "cnl_engine_create", "cnl_engine_destroy", "cnl_engine_arena_bytes", "cnl_engine_buffer_offset", "cnl_engine_op_form",
-    "cnl_engine_upload", "cnl_engine_forward", "cnl_engine_read_buffer", "cnl_engine_write_buffer",
+    "cnl_engine_upload", "cnl_engine_forward", "cnl_engine_forward_act", "cnl_engine_read_buffer", "cnl_engine_write_buffer",
 )
 
 
@@ -100,6 +100,9 @@ def load() -> C.CDLL:
     lib.cnl_engine_forward.restype = C.c_int
     lib.cnl_engine_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                        C.POINTER(C.c_int)]
+    lib.cnl_engine_forward_act.restype = C.c_int
+    lib.cnl_engine_forward_act.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.POINTER(C.c_int)]
     lib.cnl_engine_read_buffer.restype = C.c_int
     lib.cnl_engine_read_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.cnl_engine_write_buffer.restype = C.c_int

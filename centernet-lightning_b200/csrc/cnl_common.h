@@ -22,4 +22,11 @@ int fail(int code, const char* fmt, ...);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+#ifdef __CUDACC__
+// THE logistic of this library (cnl_sigmoid, the from_logits decode, the heat-map epilogue of the forward engine): three
+// separately rounded fp32 operations, the arithmetic torch.sigmoid runs on a CUDA tensor - i.e. what the reference's
+// `.sigmoid()` (centernet_lightning/models/centernet.py:205) computes on the device.
+__device__ __forceinline__ float sigmoid32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+#endif
+
 }  // namespace cnl

@@ -51,6 +51,7 @@ struct ConvParams {
   int kh, kw, stride, pad_h, pad_w, kblocks;
   int src_c_off, dst_c_off;
   int relu;
+  int sigmoid;                  // out_mode 1 only: store 1/(1+exp(-x)) (the `.sigmoid()` the reference applies to the heat map, fused)
   int out_mode;                 // 0 = NHWC fp16 planes via TMA store, 1 = NCHW fp32 direct stores
   int cout_real;
   float wscale_inv;
@@ -609,6 +610,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             if (valid && c < p.cout_real) {
               float val = fmaf(v[j], p.wscale_inv, __ldg(p.bias + c));
               if (p.relu) val = fmaxf(val, 0.0f);
+              if (p.sigmoid) val = sigmoid32(val);         // the kernel is HBM-bound: the logistic hides behind the loads
               out_px[c * cstride] = val;
             }
           }
@@ -1245,7 +1247,14 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
 }
 
 int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first_op, int last_op, void* stream, int* launches) {
+  return cnl_engine_forward_act(e, arena, image, first_op, last_op, -1, stream, launches);
+}
+
+int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int first_op, int last_op, int sigmoid_buffer,
+                           void* stream, int* launches) {
   if (!e || !arena) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: null argument");
+  if (sigmoid_buffer >= (int)e->bufs.size() || (sigmoid_buffer >= 0 && !e->bufs[sigmoid_buffer].fp32_nchw))
+    return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward_act: sigmoid_buffer must be an fp32 NCHW output buffer");
   if (arena != e->uploaded_arena) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: call cnl_engine_upload for this arena first");
   if (first_op < 0 || last_op > (int)e->ops.size() || first_op > last_op) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: bad op range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1288,6 +1297,7 @@ int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first
     p.m_tiles = e->batch * op.tiles_w * op.tiles_h;
     p.n_tiles = op.n_tiles; p.n_tile = op.n_tile;
     p.relu = d.relu;
+    p.sigmoid = (sigmoid_buffer >= 0 && d.dst == sigmoid_buffer) ? 1 : 0;
     p.wscale_inv = 1.0f / op.wscale;
     p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;

@@ -20,7 +20,13 @@
 #include "cnl_common.h"
 
 #ifndef CNL_NEARTIE_MODE
-#define CNL_NEARTIE_MODE 2
+#define CNL_NEARTIE_MODE 1
+#endif
+#ifndef CNL_PEAKS_PIPELINE
+#define CNL_PEAKS_PIPELINE 0      // measured on B200: prefetching the next class inside the walk costs registers (spills at 64-72) and is slower
+#endif
+#ifndef CNL_PEAKS_MINB
+#define CNL_PEAKS_MINB 8
 #endif
 
 namespace cnl {
@@ -39,8 +45,7 @@ int fail(int code, const char* fmt, ...) {
 // Scalar semantics shared by every peaks kernel
 // ------------------------------------------------------------------------------------------------------------
 
-// The logistic the from_logits path specifies: three separately rounded fp32 operations.
-__device__ __forceinline__ float sigmoid32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// (sigmoid32, the logistic the from_logits path specifies, lives in cnl_common.h)
 
 // from_logits semantics.  The reference compares PROBABILITIES (centernet.py:252-254): a pixel is kept when
 // sigmoid(x) == max over the window of sigmoid(.), and the label is the FIRST class whose kept probability equals the
@@ -98,21 +103,20 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
   return __uint_as_float(b);
 }
-constexpr int kHistBins = 4096;             // per-image histogram of candidate keys (top 12 bits), built by kernel 1
-constexpr int kHistShift = 20;
-
-// Histogram update of one candidate per lane (whole warp, converged).  Pixels without any peak keep the initial value
-// (probability 0): they are NOT counted - smooth maps have thousands of them per image and they would all hit one address;
-// the select kernel recovers their number as H*W minus the histogram total.  The remaining lanes are aggregated per
-// bin with match.any, so a warp issues one atomic per distinct bin.
-__device__ __forceinline__ void hist_add(unsigned int* hist_img, float v, bool valid) {
-  const bool counted = valid && (v != 0.0f);
-  const uint32_t bin = sortable_key(v) >> kHistShift;
-  const unsigned peers = __match_any_sync(0xffffffffu, counted ? bin : 0xffffffffu);
-  if (counted && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist_img + bin, (unsigned)__popc(peers));
+constexpr int kHistBins = 4096;             // per-image histogram of the candidates, built by the select kernel in shared memory
+// Candidates are probabilities.  Bin = [exponent | top 8 mantissa bits] of the float, offset so that p = 1.0f is the last
+// bin and everything below 2^-16 the first: 256 bins per octave between 2^-16 and 1 (0.4 % wide - the top-k of a map almost
+// always ends inside one or two of them, where float's own exponent/3-mantissa-bit split put all of [0.5, 1) into 8 bins).
+// Monotone in the key; bins 1 .. kHistBins-2 hold one exponent each, so the next 11 mantissa bits refine them.
+constexpr uint32_t kBinBase = ((127u - 16u) << 8) + 1u;
+constexpr int kSubShift = 4;                // second-level digit of an un-clamped bin: key bits [14:4]
+__device__ __forceinline__ uint32_t cand_bin(uint32_t key) {
+  if (!(key & 0x80000000u)) return 0u;                        // negative inputs (not probabilities) sort below everything
+  const int v = (int)((key & 0x7fffffffu) >> 15) - (int)kBinBase;
+  return (uint32_t)min(max(v, 0), kHistBins - 1);
 }
-// bin that holds the uncounted "no peak" candidates
-constexpr int kNoPeakBin = 2048;             // key(0.f) = 0x80000000
+
+constexpr int kNoPeakBin = 0;                // cand_bin(key(0.f)): pixels without any peak
 
 // ------------------------------------------------------------------------------------------------------------
 // Kernel 1a: fast streaming peaks kernel (W % 4 == 0).  One warp = RxTW pixel strip x one class group.
@@ -132,13 +136,22 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 // Class loop of one warp: rows [r0-P, r0+R+P) x columns [x0-P, x0+4*VEC+P) of classes [c_begin, c_end).
 // A lane owns 4*VEC consecutive columns (VEC float4 loads per row), the warp a tile of 128*VEC columns.
 // EDGE=false is the interior fast path (every row and column of the strip is inside the map: no predicates).
-// LOGITS: the fast pass applies the x == m test and tracks the smallest non-zero gap m - x it saw; only when some lane's
-// gap is below collapse_thr (a near tie: see the semantics note above) the class is walked a second time with the exact
-// probability test for the centres below their window max.
-template <int P, bool LOGITS, int R, bool MT, bool EDGE, int VEC>
+//
+// CNL_PEAKS_PIPELINE=1 (build-time experiment, off): output row i reads strip rows i .. i+2P, so strip row i is dead once
+// output row i is done and can be refilled with the SAME row of the NEXT class right there (loads in flight while the
+// warp computes, without a second set of registers).  Measured on B200 at 32x80x128x128: 32.3 us against 28.3 us for the
+// plain load-then-walk loop - the extra address registers spill at the 64-register budget that keeps 8 CTAs per SM.
+//
+// LOGITS: the walk applies the x == m test and tracks the smallest non-zero gap m - x; only when some lane of the warp saw
+// a near tie (see the semantics note above) the class is re-read and walked a second time with the exact probability
+// test for the centres below their window max.
+// WC: compile-time row length (128, the 512x512-input map) or 0 = runtime W; a constant turns every row offset into an
+// immediate and frees the registers the pipelined loads need.
+template <int P, bool LOGITS, int R, bool MT, bool EDGE, int VEC, int WC>
 __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base, size_t plane, int c_begin, int c_end,
-                                                 int H, int W, int r0, int x0, int lane,
+                                                 int H, int W_rt, int r0, int x0, int lane,
                                                  float (&best)[R][4 * VEC]) {
+  const int W = WC ? WC : W_rt;
   constexpr int ROWS = R + 2 * P;
   constexpr int PH = (P > 0) ? P : 1;
   constexpr int NC = 4 * VEC;                        // columns per lane
@@ -150,151 +163,146 @@ __device__ __forceinline__ void peaks_class_loop(const float* __restrict__ base,
 #pragma unroll
   for (int u = 0; u < VEC; ++u) col_ok[u] = !EDGE || (x0 + 4 * u < W);
   const float edge_l = (lane == 0) ? NEG : 0.0f, edge_r = (lane == 31) ? NEG : 0.0f;
+  // Halo columns of neighbouring column tiles (rows wider than one warp tile).  The neighbour shuffles of the walk are
+  // rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the right" shuffle are
+  // free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
+  const bool halo_lane = (lane == 0 || lane == 31);
 
+  float4 v[ROWS][VEC];
+  float hx[ROWS][PH];
+  auto load_row = [&](const float* pl, int j) {
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) {
+      if (EDGE) v[j][u] = (row_ok[j] && col_ok[u]) ? ld_stream4(pl + (long long)j * W + 4 * u) : make_float4(NEG, NEG, NEG, NEG);
+      else      v[j][u] = ld_stream4(pl + (long long)j * W + 4 * u);
+    }
+    if constexpr (P > 0 && MT) {
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        hx[j][q] = NEG;
+        const int xt = (lane == 31) ? (x0 - 31 * NC - 1 - q) : (x0 + 32 * NC + q);     // tile's first column - 1 - q / last + 1 + q
+        if (halo_lane && row_ok[j] && xt >= 0 && xt < W) hx[j][q] = __ldg(pl + (long long)j * W + (xt - x0));
+      }
+    }
+  };
+  auto load_strip = [&](const float* pl) {
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) load_row(pl, j);
+  };
+
+  if (c_begin >= c_end) return;
+#if CNL_PEAKS_PIPELINE
+  load_strip(base + (size_t)c_begin * plane);
+#endif
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const float* pl = base + (size_t)c * plane;
-    float4 v[ROWS][VEC];
-    float hx[ROWS][PH];
-    auto load_strip = [&]() {
+    const float* pl_next = pl + plane;
+#if CNL_PEAKS_PIPELINE
+    const bool has_next = (c + 1 < c_end);
+#else
+    const bool has_next = false;
+    load_strip(pl);
+#endif
+    // Near-tie detector of the fast walk: the smallest non-zero gap m - x it saw, compared after the walk with the collapse
+    // bound of the largest window max this lane can have met (the vertical maxima of its own columns, its neighbour lanes'
+    // and the halo columns).  CNL_NEARTIE_MODE 0 disables it (timing experiments only: not reference-exact).
+    float gap = INFINITY;
+    float tmax = -INFINITY;
+    // one output row; EXACT = false: x == m test (+ detector), EXACT = true: probability test for the centres that are
+    // below their window max by less than thr
+    auto walk_row = [&](auto exact_tag, int i, float thr) {
+      constexpr bool EXACT = decltype(exact_tag)::value;
+      // vertical max over the window rows
+      float4 vm[VEC];
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j)
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) {
-          if (EDGE) v[j][u] = (row_ok[j] && col_ok[u]) ? ld_stream4(pl + (long long)j * W + 4 * u) : make_float4(NEG, NEG, NEG, NEG);
-          else      v[j][u] = ld_stream4(pl + (long long)j * W + 4 * u);
-        }
-      // Halo columns of neighbouring column tiles (rows wider than one warp tile).  The neighbour shuffles below are
-      // rotations, so lane 31's slot in the "from the left" shuffle and lane 0's slot in the "from the right" shuffle
-      // are free: lane 31 carries the tile's LEFT halo columns, lane 0 its RIGHT halo columns.
+      for (int u = 0; u < VEC; ++u) vm[u] = v[i][u];
+      float vh[PH];
       if constexpr (P > 0 && MT) {
 #pragma unroll
-        for (int j = 0; j < ROWS; ++j)
-#pragma unroll
-          for (int q = 0; q < P; ++q) {
-            hx[j][q] = NEG;
-            const int xt = (lane == 31) ? (x0 - 31 * NC - 1 - q) : (x0 + 32 * NC + q);     // tile's first column - 1 - q / last + 1 + q
-            if ((lane == 0 || lane == 31) && row_ok[j] && xt >= 0 && xt < W) hx[j][q] = __ldg(pl + (long long)j * W + (xt - x0));
-          }
+        for (int q = 0; q < P; ++q) vh[q] = hx[i][q];
       }
-    };
-    load_strip();
-    int thr_e = 0;                                   // exponent of the near-tie threshold of this lane's strip (kNoBound: none)
-    if constexpr (LOGITS && P > 0) {
-      // largest logit this lane can see as a window max: its own columns, its neighbour lanes' and the halo columns
-      float4 t4 = v[0][0];
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j)
+      for (int j = 1; j <= 2 * P; ++j) {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) t4 = max4(t4, v[j][u]);
-      float tmax = fmaxf(fmaxf(t4.x, t4.y), fmaxf(t4.z, t4.w));
-      if constexpr (MT) {
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j)
-#pragma unroll
-          for (int q = 0; q < P; ++q) tmax = fmaxf(tmax, hx[j][q]);
-      }
-      const float tl = __shfl_sync(0xffffffffu, tmax, (lane + 31) & 31), tr = __shfl_sync(0xffffffffu, tmax, (lane + 1) & 31);
-      thr_e = collapse_exp(fmaxf(tmax, fmaxf(tl, tr)));
-    }
-    // one walk over the strip's rows; EXACT = false: x == m test (+ smallest non-zero gap), EXACT = true: probability test
-    // for the centres that are below their window max by less than thr
-    // near-tie detector of the fast walk.  CNL_NEARTIE_MODE 1: smallest non-zero gap m - x (FSEL + FMNMX on the ALU pipe,
-    // the pipe this kernel loads most); mode 2: FMA-pipe only - g = sat((m - x) / thr) is 0 for a peak, 1 for a clear
-    // non-peak and strictly in between for a near tie, so acc = sum g (1 - g) is non-zero iff the strip holds one
-    // (every term is >= 0: no cancellation; denormal gaps keep g > 0 because thr <= 2^7).
-    float gap = INFINITY;
-    float acc = 0.0f;
-    const float inv_thr = (thr_e == kNoBound) ? 0.0f : pow2f(-thr_e);
-    auto walk = [&](auto exact_tag, float thr) {
-      constexpr bool EXACT = decltype(exact_tag)::value;
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        // vertical max over the window rows
-        float4 vm[VEC];
-#pragma unroll
-        for (int u = 0; u < VEC; ++u) vm[u] = v[i][u];
-        float vh[PH];
+        for (int u = 0; u < VEC; ++u) vm[u] = max4(vm[u], v[i + j][u]);
         if constexpr (P > 0 && MT) {
 #pragma unroll
-          for (int q = 0; q < P; ++q) vh[q] = hx[i][q];
+          for (int q = 0; q < P; ++q) vh[q] = fmaxf(vh[q], hx[i + j][q]);
         }
+      }
+      if constexpr (LOGITS && P > 0 && !EXACT && CNL_NEARTIE_MODE != 0) {
 #pragma unroll
-        for (int j = 1; j <= 2 * P; ++j) {
+        for (int u = 0; u < VEC; ++u) tmax = fmaxf(fmaxf(tmax, fmaxf(vm[u].x, vm[u].y)), fmaxf(vm[u].z, vm[u].w));
+        if constexpr (MT) {
 #pragma unroll
-          for (int u = 0; u < VEC; ++u) vm[u] = max4(vm[u], v[i + j][u]);
-          if constexpr (P > 0 && MT) {
-#pragma unroll
-            for (int q = 0; q < P; ++q) vh[q] = fmaxf(vh[q], hx[i + j][q]);
-          }
+          for (int q = 0; q < P; ++q) tmax = fmaxf(tmax, vh[q]);
         }
-        // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+NC-1] own, e[P+NC..] right neighbours
-        float e[NC + 2 * P];
+      }
+      // horizontal: e[0..P-1] left neighbours (nearest last), e[P..P+NC-1] own, e[P+NC..] right neighbours
+      float e[NC + 2 * P];
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) {
-          e[P + 4 * u + 0] = vm[u].x; e[P + 4 * u + 1] = vm[u].y; e[P + 4 * u + 2] = vm[u].z; e[P + 4 * u + 3] = vm[u].w;
+      for (int u = 0; u < VEC; ++u) {
+        e[P + 4 * u + 0] = vm[u].x; e[P + 4 * u + 1] = vm[u].y; e[P + 4 * u + 2] = vm[u].z; e[P + 4 * u + 3] = vm[u].w;
+      }
+      if constexpr (P > 0) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          // q-th column to the left of x0 is the (NC-1-q)-th column of lane-1; to the right of x0+NC-1 it is column q of lane+1
+          float src_l = e[P + NC - 1 - q], src_r = e[P + q];
+          if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
+          float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
+          float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
+          if constexpr (!MT) { fl += edge_l; fr += edge_r; }      // -inf beyond the row ends (FADD: keeps the ALU pipe free)
+          e[P - 1 - q] = fl;
+          e[P + NC + q] = fr;
         }
-        if constexpr (P > 0) {
+      }
 #pragma unroll
-          for (int q = 0; q < P; ++q) {
-            // q-th column to the left of x0 is the (NC-1-q)-th column of lane-1; to the right of x0+NC-1 it is column q of lane+1
-            float src_l = e[P + NC - 1 - q], src_r = e[P + q];
-            if constexpr (MT) { src_l = (lane == 31) ? vh[q] : src_l; src_r = (lane == 0) ? vh[q] : src_r; }
-            float fl = __shfl_sync(0xffffffffu, src_l, (lane + 31) & 31);
-            float fr = __shfl_sync(0xffffffffu, src_r, (lane + 1) & 31);
-            if constexpr (!MT) { fl += edge_l; fr += edge_r; }      // -inf beyond the row ends (FADD: keeps the ALU pipe free)
-            e[P - 1 - q] = fl;
-            e[P + NC + q] = fr;
-          }
-        }
+      for (int u = 0; u < VEC; ++u) {
+        const float ctr[4] = {v[i + P][u].x, v[i + P][u].y, v[i + P][u].z, v[i + P][u].w};
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) {
-          const float ctr[4] = {v[i + P][u].x, v[i + P][u].y, v[i + P][u].z, v[i + P][u].w};
+        for (int j = 0; j < 4; ++j) {
+          float m = e[4 * u + j];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float m = e[4 * u + j];
-#pragma unroll
-            for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[4 * u + j + q]);
-            if constexpr (!EXACT) {
-              masked_max<LOGITS>(best[i][4 * u + j], ctr[j], m);
-              if constexpr (LOGITS && P > 0) {
-#if CNL_NEARTIE_MODE == 1
-                gap = fminf(gap, (ctr[j] == m) ? INFINITY : m - ctr[j]);
-#elif CNL_NEARTIE_MODE == 2
-                const float gq = __saturatef((m - ctr[j]) * inv_thr);          // NaN (out-of-map centre) saturates to 0
-                acc = fmaf(-gq, gq, acc + gq);
-#endif
-              }
-            } else {
-              // (an out-of-map centre is -inf: m - ctr = inf or NaN, never below thr)
-              if (ctr[j] != m && m - ctr[j] < thr && same_probability(ctr[j], m)) best[i][4 * u + j] = fmaxf(best[i][4 * u + j], ctr[j]);
-            }
+          for (int q = 1; q <= 2 * P; ++q) m = fmaxf(m, e[4 * u + j + q]);
+          if constexpr (!EXACT) {
+            masked_max<LOGITS>(best[i][4 * u + j], ctr[j], m);
+            if constexpr (LOGITS && P > 0 && CNL_NEARTIE_MODE != 0) gap = fminf(gap, (ctr[j] == m) ? INFINITY : m - ctr[j]);
+          } else {
+            // (an out-of-map centre is -inf: m - ctr = inf or NaN, never below thr)
+            if (ctr[j] != m && m - ctr[j] < thr && same_probability(ctr[j], m)) best[i][4 * u + j] = fmaxf(best[i][4 * u + j], ctr[j]);
           }
         }
       }
     };
-    walk(std::false_type{}, 0.0f);
-    if constexpr (LOGITS && P > 0) {
-      const float thr = (thr_e == kNoBound) ? INFINITY : pow2f(thr_e);
-#if CNL_NEARTIE_MODE == 1
-      const bool near = gap < thr;
-#elif CNL_NEARTIE_MODE == 2
-      const bool near = (acc > 0.0f) || (thr_e == kNoBound);
-#else
-      const bool near = false;                        // (timing experiments only: round-1 behaviour, not reference-exact)
-#endif
-      if (__any_sync(0xffffffffu, near)) {            // near tie somewhere in this warp's strip: rare
-        load_strip();                                // (re-read from L2: the strip's registers were released during the walk)
-        walk(std::true_type{}, thr);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      walk_row(std::false_type{}, i, 0.0f);
+      if (has_next) load_row(pl_next, i);            // strip row i is dead: refill it with the next class (prefetch)
+    }
+    if (has_next) {
+#pragma unroll
+      for (int j = R; j < ROWS; ++j) load_row(pl_next, j);
+    }
+    if constexpr (LOGITS && P > 0 && CNL_NEARTIE_MODE != 0) {
+      const float tl = __shfl_sync(0xffffffffu, tmax, (lane + 31) & 31), tr = __shfl_sync(0xffffffffu, tmax, (lane + 1) & 31);
+      const float thr = collapse_thr(fmaxf(tmax, fmaxf(tl, tr)));
+      if (__any_sync(0xffffffffu, gap < thr)) {       // near tie somewhere in this warp's strip: rare
+        load_strip(pl);                               // re-read this class from L2 (its registers hold the next one by now)
+#pragma unroll
+        for (int i = 0; i < R; ++i) walk_row(std::true_type{}, i, thr);
+        if (has_next) load_strip(pl_next);
       }
     }
   }
 }
 
-template <int P, bool LOGITS, int R, int G, bool MT, int VEC>
-__global__ void __launch_bounds__(G * 32, (R * VEC <= 4) ? 8 : 4)
+template <int P, bool LOGITS, int R, int G, bool MT, int VEC, int WC = 0>
+__global__ void __launch_bounds__(G * 32, (R * VEC <= 4) ? CNL_PEAKS_MINB : 4)
 peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uint8_t* __restrict__ cgroup,
-                  unsigned int* __restrict__ hist, int C, int H, int W) {
+                  int C, int H, int W_rt) {
+  const int W = WC ? WC : W_rt;
   constexpr int NC = 4 * VEC;
   constexpr int TW = kTW * VEC;                  // columns per warp tile
   const int lane = threadIdx.x & 31;
@@ -315,8 +323,8 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uin
 
   const float* base = heat + (size_t)n * C * plane + (long long)(r0 - P) * W + x0;
   const bool interior = (r0 - P >= 0) && (r0 + R + P <= H) && ((int)(blockIdx.x + 1) * TW <= W);   // block-uniform
-  if (interior) peaks_class_loop<P, LOGITS, R, MT, false, VEC>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
-  else          peaks_class_loop<P, LOGITS, R, MT, true, VEC>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
+  if (interior) peaks_class_loop<P, LOGITS, R, MT, false, VEC, WC>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
+  else          peaks_class_loop<P, LOGITS, R, MT, true, VEC, WC>(base, plane, c_begin, c_end, H, W, r0, x0, lane, best);
 
   // every CTA is past its streaming loop: the select kernel's CTAs may be scheduled while this grid drains (they wait
   // in griddepcontrol.wait until this grid has completed and flushed)
@@ -363,7 +371,6 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uin
           bv[j] = best[i][4 * u + j];
         }
         bv[j] = best_to_prob<LOGITS>(bv[j]);
-        hist_add(hist + (size_t)n * kHistBins, bv[j], ok);
       }
       if (ok) {
         *reinterpret_cast<uint32_t*>(cgroup + (size_t)n * plane + (size_t)r * W + xu) = grp;
@@ -379,7 +386,7 @@ peaks_fast_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uin
 template <bool LOGITS>
 __global__ void __launch_bounds__(256)
 peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cbest, uint8_t* __restrict__ cgroup,
-                     unsigned int* __restrict__ hist, int C, int H, int W, int P) {
+                     int C, int H, int W, int P) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int n = blockIdx.z;
@@ -404,8 +411,6 @@ peaks_generic_kernel(const float* __restrict__ heat, float* __restrict__ cbest, 
   best = best_to_prob<LOGITS>(best);
   cbest[(size_t)n * plane + (size_t)y * W + x] = best;
   cgroup[(size_t)n * plane + (size_t)y * W + x] = 0xff;
-  if (best != 0.0f)          // no-peak pixels are not counted (see hist_add)
-    atomicAdd(hist + (size_t)n * kHistBins + (sortable_key(best) >> kHistShift), 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -420,7 +425,6 @@ constexpr int kSelThreads = 1024;
 constexpr int kMaxK = 1024;
 constexpr int kListCap = 2048;
 constexpr int kBins = 2048;
-constexpr int kSubShift = kHistShift - 11;   // second-level digit: the next 11 key bits
 constexpr int kRefineAbove = 256;
 constexpr int kLabelBatch = 3;               // classes per lane and batch in the label recovery (8 lanes x 3 = 24 classes at once)            // sort directly when bin_k-and-above holds at most this many
 
@@ -513,7 +517,7 @@ __global__ void sigmoid_kernel(const float* __restrict__ in, float* __restrict__
 }
 
 struct DecodeParams {
-  const float* cscore; unsigned int* hist;           // per-pixel best masked value (logit or probability) + its histogram (zeroed again by the select kernel)
+  const float* cscore;                               // per-pixel best kept probability (0 = no peak)
   const float* heat; int C, P, from_logits;          // the head map itself: labels are recovered for the k winners only
   const uint8_t* cgroup; int group_classes;          // class group (of group_classes classes) that holds the winner; 255 = unknown
   const float* box; const float* reid;
@@ -636,7 +640,7 @@ template <bool CACHE>
 __global__ void __launch_bounds__(kSelThreads)
 select_gather_kernel(DecodeParams p) {
   __shared__ unsigned long long s_list[kListCap];
-  __shared__ __align__(8) int s_hist[kBins];
+  __shared__ __align__(16) int s_hist[kHistBins];      // first level: 4096 bins of cand_bin; reused (2048 entries) by the refinement / fallback
   __shared__ int s_warp[32];
   __shared__ int s_scalars[3];
   __shared__ int s_n;
@@ -648,6 +652,7 @@ select_gather_kernel(DecodeParams p) {
   const int n = blockIdx.x;
   const int tid = threadIdx.x;
   const int HW = p.H * p.W;
+  *reinterpret_cast<int4*>(&s_hist[4 * tid]) = make_int4(0, 0, 0, 0);
   // launched with programmatic stream serialization: this grid may start while the peaks kernel drains; nothing the
   // peaks kernel wrote may be read before it has completed and flushed
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -719,23 +724,91 @@ select_gather_kernel(DecodeParams p) {
     }
   };
 
-  // ---- bin of the k-th largest key from kernel 1's histogram (thread t owns the 4 bins 4092-4t .. 4095-4t) ----
-  uint4* my_bins = reinterpret_cast<uint4*>(p.hist + (size_t)n * kHistBins + (kHistBins - 4 - 4 * tid));
-  const uint4 h4 = *my_bins;
-  *my_bins = make_uint4(0u, 0u, 0u, 0u);         // leave the histogram clean for the next decode on this workspace
-  int cnt[4] = {(int)h4.w, (int)h4.z, (int)h4.y, (int)h4.x};            // descending bin order
-  int sum4 = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  // collect(pred): append every candidate whose key satisfies pred to s_list.  Winners are ~1 % of the candidates, so the
+  // 16 candidates a thread holds are first only counted (one compare each); a warp scan of the counts gives every lane its
+  // write position behind ONE shared-memory atomic per warp and chunk.
+  auto collect_chunk = [&](const uint32_t (&u)[16], const int (&idx)[16], const bool (&ok)[16], const uint32_t (&grp)[16], auto&& pred) {
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) c += (ok[q] && pred(u[q])) ? 1 : 0;
+    if (!__any_sync(0xffffffffu, c != 0)) return;
+    const int lane = tid & 31;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&s_n, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int pos = base + incl - c;
+    if (c == 0) return;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (ok[q] && pred(u[q])) {
+        s_list[pos] = pack_entry(u[q], idx[q]);
+        if (CACHE) s_grp_in[pos] = (uint8_t)grp[q];
+        ++pos;
+      }
+  };
+  auto collect = [&](auto&& pred) {
+    uint32_t u[16], grp[16];
+    int idx[16];
+    bool ok[16];
+    if (CACHE) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + q * kSelThreads;
+        const float fv[4] = {cache[q].x, cache[q].y, cache[q].z, cache[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          u[4 * q + j] = sortable_key(fv[j]); idx[4 * q + j] = 4 * i + j; ok[4 * q + j] = i < n_vec; grp[4 * q + j] = (cgrp[q] >> (8 * j)) & 0xffu;
+        }
+      }
+      collect_chunk(u, idx, ok, grp, pred);
+    } else {
+      for (int i0 = 0; i0 < n_vec; i0 += 4 * kSelThreads) {        // uniform trip count
+        float4 v4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * kSelThreads + tid;
+          v4[q] = (i < n_vec) ? sc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q * kSelThreads + tid;
+          const float fv[4] = {v4[q].x, v4[q].y, v4[q].z, v4[q].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { u[4 * q + j] = sortable_key(fv[j]); idx[4 * q + j] = 4 * i + j; ok[4 * q + j] = i < n_vec; grp[4 * q + j] = 0xffu; }
+        }
+        collect_chunk(u, idx, ok, grp, pred);
+      }
+      for (int i0 = 4 * n_vec; i0 < HW; i0 += kSelThreads) {         // maps whose size is not a multiple of 4 (small, generic kernel)
+        const int i = i0 + tid;
+        const bool in = i < HW;
+        const uint32_t uu = sortable_key(in ? sc[i] : 0.f);
+        append(in && pred(uu), pack_entry(uu, i), 0xffu);
+      }
+    }
+  };
+  // smallest sortable key of a histogram bin (bin 0 holds everything below 2^-16, negative inputs included)
+  auto bin_floor_key = [](uint32_t bin) -> uint32_t { return bin == 0 ? 0u : (0x80000000u | ((bin + kBinBase) << 15)); };
+
+  // ---- histogram of the image's candidates (shared memory), then the bin of the k-th largest (thread t owns the 4 bins
+  //      4092-4t .. 4095-4t).  Pixels without a peak (probability 0, often the majority) are counted per warp, not per pixel.
+  __syncthreads();                                   // s_hist was zeroed before the dependency wait
   {
-    // pixels without a peak were not counted by kernel 1 (hist_add): they all sit in one known bin
-    const int total = block_inclusive_scan(sum4, s_warp);      // inclusive -> last thread holds the sum
-    __shared__ int s_total;
-    if (tid == kSelThreads - 1) s_total = total;
-    __syncthreads();
-    const int missing = HW - s_total;
-    const int nb = kNoPeakBin;
-    const int owner = (kHistBins - 1 - nb) >> 2, slot = (kHistBins - 1 - nb) & 3;            // thread / position of that bin
-    if (tid == owner) { cnt[slot] += missing; sum4 += missing; }
+    int zeros = 0;
+    visit([&](uint32_t u, int i, bool ok, uint32_t g) {
+      if (!ok) return;
+      if (u == 0x80000000u) ++zeros; else atomicAdd(&s_hist[cand_bin(u)], 1);
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if ((tid & 31) == 0 && zeros) atomicAdd(&s_hist[kNoPeakBin], zeros);
   }
+  __syncthreads();
+  const int4 h4 = *reinterpret_cast<const int4*>(&s_hist[kHistBins - 4 - 4 * tid]);
+  int cnt[4] = {h4.w, h4.z, h4.y, h4.x};            // descending bin order
+  int sum4 = cnt[0] + cnt[1] + cnt[2] + cnt[3];
   const unsigned long long* s_sorted = s_list;
   bool have_grp = false;                             // s_grp_sorted[j] = class group of winner j
   if (k > kMaxK) {
@@ -764,17 +837,19 @@ select_gather_kernel(DecodeParams p) {
   bool done = false;
   if (n_in_or_above <= kRefineAbove) {
     // few enough: collect every candidate in bin_k or above and sort them all
-    visit([&](uint32_t u, int i, bool ok, uint32_t g) { append(ok && (u >> kHistShift) >= bin_k, pack_entry(u, i), g); });
+    const uint32_t floor_k = bin_floor_key(bin_k);
+    collect([&](uint32_t u) { return u >= floor_k; });
     n_sort = n_in_or_above;
     done = true;
-  } else {
-    // Scores crowd into bin_k (e.g. probabilities close to 1): refine with the next 11 key bits.  One pass
+  } else if (bin_k > 0 && bin_k < (uint32_t)(kHistBins - 1)) {
+    // Scores crowd into bin_k: refine with the next 11 key bits (the clamped end bins span several exponents and go to the
+    // exact radix select below instead).  One pass
     // collects everything above bin_k and histograms the members of bin_k; a second pass collects the members
     // of bin_k at or above the sub-bin that holds the k-th largest.
     for (int i = tid; i < kBins; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
     visit([&](uint32_t u, int i, bool ok, uint32_t g) {
-      const uint32_t b = u >> kHistShift;
+      const uint32_t b = cand_bin(u);
       append(ok && b > bin_k, pack_entry(u, i), g);
       if (ok && b == bin_k) atomicAdd(&s_hist[(u >> kSubShift) & (kBins - 1)], 1);
     });
@@ -793,9 +868,10 @@ select_gather_kernel(DecodeParams p) {
     const uint32_t sub_k = (uint32_t)s_scalars[0];
     const int n_total = n_above + s_scalars[1];
     if (n_total <= kListCap) {
-      visit([&](uint32_t u, int i, bool ok, uint32_t g) {
-        append(ok && (u >> kHistShift) == bin_k && ((u >> kSubShift) & (kBins - 1)) >= sub_k, pack_entry(u, i), g);
-      });
+      // members of bin_k at or above sub-bin sub_k: one key interval (an un-clamped bin is one exponent, so its keys order
+      // like their mantissa bits)
+      const uint32_t lo_k = bin_floor_key(bin_k) | (sub_k << kSubShift), hi_k = bin_floor_key(bin_k + 1);
+      collect([&](uint32_t u) { return u >= lo_k && u < hi_k; });
       n_sort = n_total;
       done = true;
     }
@@ -936,14 +1012,16 @@ select_gather_kernel(DecodeParams p) {
 // L2 traffic at R = 4, 25 % at R = 8), VEC = float4 loads per lane and row (warp tile = 128*VEC columns; rows of up to
 // 256 columns then need no halo columns from a neighbouring tile).  CNL_PEAKS_R / CNL_PEAKS_VEC override the choice.
 template <int P, bool LOGITS, int R, int VEC>
-static int launch_fast_rv(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+static int launch_fast_rv(const float* heat, float* cscore, uint8_t* cgroup, int N, int C, int H, int W,
                           cudaStream_t st) {
   dim3 grid((W + kTW * VEC - 1) / (kTW * VEC), (H + R - 1) / R, N);
   const bool mt = grid.x > 1;        // rows wider than one warp tile need halo columns from neighbours
 #define CNL_LAUNCH_PEAKS(G_)                                                                                      \
   do {                                                                                                            \
-    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true, VEC><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W);  \
-    else    peaks_fast_kernel<P, LOGITS, R, G_, false, VEC><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, hist, C, H, W); \
+    if (mt) peaks_fast_kernel<P, LOGITS, R, G_, true, VEC><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, C, H, W);  \
+    else if (P == 1 && VEC == 1 && R == 4 && W == kTW)                                                             \
+      peaks_fast_kernel<P, LOGITS, R, G_, false, VEC, (P == 1 && VEC == 1 && R == 4) ? kTW : 0><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, C, H, W); \
+    else    peaks_fast_kernel<P, LOGITS, R, G_, false, VEC><<<grid, G_ * 32, 0, st>>>(heat, cscore, cgroup, C, H, W); \
   } while (0)
   int groups = 1;
   if (C >= 32) { CNL_LAUNCH_PEAKS(4); groups = 4; }
@@ -954,7 +1032,7 @@ static int launch_fast_rv(const float* heat, float* cscore, uint8_t* cgroup, uns
 }
 
 template <int P, bool LOGITS>
-static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, int N, int C, int H, int W,
                        cudaStream_t st) {
   static const int env_r = getenv("CNL_PEAKS_R") ? atoi(getenv("CNL_PEAKS_R")) : 0;
   static const int env_v = getenv("CNL_PEAKS_VEC") ? atoi(getenv("CNL_PEAKS_VEC")) : 0;
@@ -963,26 +1041,26 @@ static int launch_fast(const float* heat, float* cscore, uint8_t* cgroup, unsign
   int rows = 4;
   if (env_r == 4 || env_r == 8) rows = env_r;
   if constexpr (P == 1) {
-    if (vec == 2) return launch_fast_rv<P, LOGITS, 4, 2>(heat, cscore, cgroup, hist, N, C, H, W, st);
-    if (rows == 8) return launch_fast_rv<P, LOGITS, 8, 1>(heat, cscore, cgroup, hist, N, C, H, W, st);
+    if (vec == 2) return launch_fast_rv<P, LOGITS, 4, 2>(heat, cscore, cgroup, N, C, H, W, st);
+    if (rows == 8) return launch_fast_rv<P, LOGITS, 8, 1>(heat, cscore, cgroup, N, C, H, W, st);
   }
-  return launch_fast_rv<P, LOGITS, 4, 1>(heat, cscore, cgroup, hist, N, C, H, W, st);
+  return launch_fast_rv<P, LOGITS, 4, 1>(heat, cscore, cgroup, N, C, H, W, st);
 }
 
 // returns the number of classes per recorded class group (0 = no group information, scan every class)
 template <bool LOGITS>
-static int launch_peaks(const float* heat, float* cscore, uint8_t* cgroup, unsigned int* hist, int N, int C, int H, int W,
+static int launch_peaks(const float* heat, float* cscore, uint8_t* cgroup, int N, int C, int H, int W,
                         int P, bool force_generic, cudaStream_t st) {
   bool fast = !force_generic && (W % 4 == 0) && P <= 2 && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   if (fast) {
     switch (P) {
-      case 0: return launch_fast<0, LOGITS>(heat, cscore, cgroup, hist, N, C, H, W, st);
-      case 1: return launch_fast<1, LOGITS>(heat, cscore, cgroup, hist, N, C, H, W, st);
-      case 2: return launch_fast<2, LOGITS>(heat, cscore, cgroup, hist, N, C, H, W, st);
+      case 0: return launch_fast<0, LOGITS>(heat, cscore, cgroup, N, C, H, W, st);
+      case 1: return launch_fast<1, LOGITS>(heat, cscore, cgroup, N, C, H, W, st);
+      case 2: return launch_fast<2, LOGITS>(heat, cscore, cgroup, N, C, H, W, st);
     }
   }
   dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-  peaks_generic_kernel<LOGITS><<<grid, 256, 0, st>>>(heat, cscore, cgroup, hist, C, H, W, P);
+  peaks_generic_kernel<LOGITS><<<grid, 256, 0, st>>>(heat, cscore, cgroup, C, H, W, P);
   return 0;
 }
 
@@ -1051,20 +1129,16 @@ int cnl_decode_detections_packed(const float* heatmap, const float* box_offsets,
     return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_decode_detections: boxes must be 16-byte aligned");
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned int* hist = static_cast<unsigned int*>(workspace);
   float* cscore = reinterpret_cast<float*>(static_cast<char*>(workspace) + hist_bytes(n));
   const int P = (nms_kernel - 1) / 2;
-  // the select kernel zeroes the histogram after reading it, so a workspace that was last used by a completed decode of the
-  // same batch size needs no memset (CNL_DECODE_WORKSPACE_CLEAN); a fresh or foreign workspace does
-  if (!workspace_clean && !peaks_only) CNL_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)n * kHistBins * sizeof(unsigned int), st));
   uint8_t* cgroup = reinterpret_cast<uint8_t*>(static_cast<char*>(workspace) + hist_bytes(n) + score_bytes(n, h, w));
-  const int group_classes = from_logits ? launch_peaks<true>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st)
-                                        : launch_peaks<false>(heatmap, cscore, cgroup, hist, n, c, h, w, P, force_generic, st);
+  const int group_classes = from_logits ? launch_peaks<true>(heatmap, cscore, cgroup, n, c, h, w, P, force_generic, st)
+                                        : launch_peaks<false>(heatmap, cscore, cgroup, n, c, h, w, P, force_generic, st);
   CNL_CUDA_CHECK(cudaGetLastError());
   if (peaks_only) return CNL_OK;
 
   DecodeParams p;
-  p.cscore = cscore; p.hist = hist; p.box = box_offsets; p.reid = reid;
+  p.cscore = cscore; p.box = box_offsets; p.reid = reid;
   p.heat = heatmap; p.C = c; p.P = P; p.from_logits = from_logits ? 1 : 0;
   p.cgroup = cgroup; p.group_classes = group_classes;
   p.H = h; p.W = w; p.E = reid_dim; p.k = num_detections;

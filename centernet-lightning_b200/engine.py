@@ -78,9 +78,11 @@ class Engine:
         n = self.batch * b.channels * h * w
         return self.arena[off:off + 4 * n].view(torch.float32).view(self.batch, b.channels, h, w)
 
-    def forward(self, image: torch.Tensor, first_op: int = 0, last_op: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    def forward(self, image: torch.Tensor, first_op: int = 0, last_op: Optional[int] = None,
+                sigmoid_head: Optional[str] = None) -> Dict[str, torch.Tensor]:
         """Runs the op range on the current stream.  Returns views of the head outputs inside the arena
-        (valid until the next forward)."""
+        (valid until the next forward).  ``sigmoid_head``: that head's out-conv stores probabilities (the reference's
+        ``.sigmoid()`` of models/centernet.py:205 fused into its epilogue) instead of logits."""
         if image is not None:
             if tuple(image.shape) != (self.batch, 3, self.height, self.width):
                 raise ValueError(f"image must be {(self.batch, 3, self.height, self.width)}, got {tuple(image.shape)}")
@@ -90,9 +92,10 @@ class Engine:
             raise RuntimeError("this engine was closed (its model's weights were reloaded): ask the model for a new one")
         n = C.c_int(0)
         with torch.cuda.device(self.device):        # launches go to the engine's device whatever the caller's current one is
-            st = self.lib.cnl_engine_forward(self.handle, self.arena.data_ptr(), image.data_ptr() if image is not None else None,
-                                             first_op, self.num_ops if last_op is None else last_op,
-                                             torch.cuda.current_stream(self.device).cuda_stream, C.byref(n))
+            sig = self.buffer_ids[self.plan.outputs[sigmoid_head]] if sigmoid_head is not None else -1
+            st = self.lib.cnl_engine_forward_act(self.handle, self.arena.data_ptr(), image.data_ptr() if image is not None else None,
+                                                 first_op, self.num_ops if last_op is None else last_op, sig,
+                                                 torch.cuda.current_stream(self.device).cuda_stream, C.byref(n))
         _lib.check(st, "cnl_engine_forward")
         self.last_launches = n.value
         return self.outputs

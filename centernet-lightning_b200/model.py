@@ -198,13 +198,14 @@ class EngineModel(nn.Module):
             self._engines.move_to_end(key)
         return eng
 
-    def forward(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def forward(self, images: torch.Tensor, sigmoid_head: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """``sigmoid_head`` (an extension): that head is returned as probabilities, the logistic fused into its out-conv."""
         if images.dim() != 4 or images.shape[1] != 3:
             raise ValueError(f"images must be (N,3,H,W), got {tuple(images.shape)}")
         if not images.is_cuda:
             raise RuntimeError("images are on the CPU: the cnl_b200 forward runs on CUDA (sm_100a) only, there is no fallback")
         images = images.float().contiguous()
-        out = self.engine_for(images).forward(images)
+        out = self.engine_for(images).forward(images, sigmoid_head=sigmoid_head)
         # fresh tensors, as the reference's GenericModel returns: the engine's own buffers are overwritten by the next call
         # with this shape (detect() reads them in place instead)
         return {k: v.clone() for k, v in out.items()}
@@ -259,11 +260,10 @@ class CenterNet(nn.Module):
 
     def forward(self, images: torch.Tensor):
         """G1 contract: (sigmoid(heatmap), box_2d[, reid])  (reference tests/test_models.py:88-99, models/tracker.py:100)."""
-        out = self.model(images)
-        heat = _decode.sigmoid(out["heatmap"])
+        out = self.model(images, sigmoid_head="heatmap")          # the logistic runs in the heat-map out-conv's epilogue
         if "reid" in out:
-            return _Trk(heat, out["box_2d"], out["reid"])
-        return _Det(heat, out["box_2d"])
+            return _Trk(out["heatmap"], out["box_2d"], out["reid"])
+        return _Det(out["heatmap"], out["box_2d"])
 
     # ---- decode (reference models/centernet.py:229-304) ----------------------------------------------------
     def decode_detections(self, heatmap: torch.Tensor, box_offsets: torch.Tensor, normalize_boxes: bool = False,
@@ -504,8 +504,10 @@ class _DetectGraph:
         outs = self.engine.outputs
         reid = outs.get("reid")
         self.bufs = _decode.DecodeBuffers(n, h, w, k, reid.shape[1] if reid is not None else 0, dev, packed=packed_out)
+        # the heat-map out-conv stores probabilities (the reference's `.sigmoid()`, models/centernet.py:205, in its epilogue),
+        # so the decode is the reference's own probability-space decode: no second pass over the map, no logit-space shortcut
         self.kw = dict(num_detections=k, nms_kernel=hp.nms_kernel, normalize_boxes=normalize_boxes, box_log=hp.box_log,
-                       box_multiplier=hp.box_multiplier, stride=net.stride, from_logits=True)
+                       box_multiplier=hp.box_multiplier, stride=net.stride, from_logits=False)
         self.launches = 0
         self.graph = None
         if not static_input:
@@ -525,7 +527,7 @@ class _DetectGraph:
                     self._body()
 
     def _body(self):
-        outs = self.engine.forward(self.static_in)
+        outs = self.engine.forward(self.static_in, sigmoid_head="heatmap")
         self.launches = self.engine.last_launches + _decode.decode_into(self.bufs, outs["heatmap"], outs["box_2d"],
                                                                          outs.get("reid"), **self.kw)
 

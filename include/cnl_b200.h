@@ -65,9 +65,8 @@ int cnl_compiled_sm(void);
 size_t cnl_decode_workspace_bytes(int n, int h, int w);
 size_t cnl_decode_workspace_bytes_k(int n, int h, int w, int num_detections);
 
-/* `from_logits` may be OR-ed with CNL_DECODE_WORKSPACE_CLEAN when the workspace was last used by a COMPLETED
- * cnl_decode_detections call with the same n (each call leaves the histogram it used zeroed); the initial memset is then
- * skipped.  Never set it for a fresh workspace. */
+/* CNL_DECODE_WORKSPACE_CLEAN: accepted for ABI compatibility and ignored (the candidate histogram lives in the select
+ * kernel's shared memory since ABI 1.1; the workspace needs no initialisation). */
 #define CNL_DECODE_WORKSPACE_CLEAN 2
 /* Profiling aid, OR-ed into `from_logits`: launch only the streaming (peaks) kernel and skip the per-image select, so that
  * the HBM-bound pass can be timed alone with CUDA events.  Outputs are not written and the workspace histogram is left
@@ -202,6 +201,13 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream);
  * to it).  CUDA-graph capturable.  Returns the number of kernels launched in *launches if non-NULL. */
 int cnl_engine_forward(cnl_engine* e, void* arena, const float* image, int first_op, int last_op,
                        void* stream, int* launches);
+
+/* The same, with the logistic 1/(1+exp(-x)) (cnl_sigmoid's arithmetic) applied by the convolution that writes fp32 output
+ * buffer `sigmoid_buffer` (-1: none) - the `.sigmoid()` the reference applies to the heat-map head before decoding
+ * (centernet_lightning/models/centernet.py:205; G1 forward(), tests/test_models.py:88-99), fused into the producing
+ * kernel's epilogue so that the decode receives probabilities without a separate pass over the map. */
+int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int first_op, int last_op,
+                           int sigmoid_buffer, void* stream, int* launches);
 
 /* Debug / test helpers: convert an NHWC-fp16(hi[,lo]) activation buffer to (N,C,H,W) fp32 and back. */
 int cnl_engine_read_buffer(cnl_engine* e, void* arena, int buffer, float* out_nchw, void* stream);

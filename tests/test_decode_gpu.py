@@ -128,12 +128,17 @@ def test_collapsed_neighbours_and_classes_follow_the_probabilities(cuda):
     """8.0 and 8.00001 share one fp32 probability (as do 12.0 / 12.0005 and 3.0 / 3.0 + 5 ulp): the reference keeps BOTH
     neighbouring pixels, and between two classes at one pixel the FIRST class wins although its logit is smaller."""
     from centernet_lightning_b200 import decode
-    for lo, hi in [(8.0, 8.00001), (12.0, 12.0005), (3.0, cases._ulps(3.0, 5))]:
+    # around 3.0 only ~8 consecutive floats share a probability: pick a run of three from the device's own logistic
+    near3 = torch.tensor([cases._ulps(3.0, i) for i in range(64)])
+    p3 = decode.sigmoid(near3.to(cuda).view(1, 1, 1, -1)).view(-1).cpu()
+    run = next(i for i in range(62) if p3[i] == p3[i + 1] == p3[i + 2])
+    for lo, hi, hi2 in [(8.0, 8.00001, cases._ulps(8.00001, 3)), (12.0, 12.0005, cases._ulps(12.0005, 3)),
+                        (near3[run].item(), near3[run + 1].item(), near3[run + 2].item())]:
         heat = torch.full((1, 2, 8, 8), -9.0)
         heat[0, 0, 2, 2] = lo
         heat[0, 0, 2, 3] = hi                     # neighbour with the larger logit, same probability
         heat[0, 0, 6, 6] = hi                     # two classes at one pixel: class 1 holds the larger logit
-        heat[0, 1, 6, 6] = cases._ulps(hi, 3)
+        heat[0, 1, 6, 6] = hi2
         heat[0, 1, 4, 0] = 0.0                    # a clearly smaller, separate peak
         p = decode.sigmoid(heat.to(cuda)).cpu()
         assert p[0, 0, 2, 2] == p[0, 0, 2, 3] and p[0, 0, 6, 6] == p[0, 1, 6, 6], "premise: these logits collapse in fp32"

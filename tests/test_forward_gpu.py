@@ -253,6 +253,27 @@ def test_config1_simple_neck_512_matches_oracle(cuda):
     assert np.array_equal(det["labels"], oracle["labels"]) and np.array_equal(det["boxes"], oracle["boxes"])
 
 
+def test_fused_sigmoid_epilogue_is_the_library_logistic(cuda):
+    """G1 forward() / detect() take the heat map as PROBABILITIES written by the out-conv's epilogue: bit-identical to
+    cnl_sigmoid of the logits model() returns, so detect() == probability-space decode of those (reference centernet.py:204-205)."""
+    from centernet_lightning_b200 import decode
+    kw = dict(model=dict(num_classes=80), seed=2, n=2, size=128, img_seed=12)
+    _, net = _build(kw)
+    net = net.to(cuda)
+    x = cases.make_image(kw).to(cuda)
+    logits = net.model(x)
+    heat, box = net(x)
+    assert torch.equal(heat, decode.sigmoid(logits["heatmap"])) and torch.equal(box, logits["box_2d"])
+    assert torch.equal(heat, torch.sigmoid(logits["heatmap"]))                     # = the device logistic the reference runs
+    det = net.detect(x)
+    ref = net.decode_detections(heat, box)
+    for k in ref:
+        assert torch.equal(det[k], ref[k]), k
+    fused = net.decode_detections(logits["heatmap"], box, from_logits=True)       # the from_logits entry point agrees as well
+    for k in ref:
+        assert torch.equal(det[k], fused[k]), k
+
+
 def test_engine_decode_bit_exact_on_engine_maps(cuda):
     """The decode half is bit-exact GIVEN the head maps (SURVEY 7 'hard parts'): run the oracle decode on the
     engine's own fp32 head outputs and compare with detect()."""

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from centernet_lightning_b200 import decode  # noqa: E402
 
 
-def run(n, c, h, w, k, iters, logits, nbuf=4, smooth=False, source=None):
+def run(n, c, h, w, k, iters, logits, nbuf=4, smooth=False, source=None, peaks_only=False):
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     bufs = [torch.randn((n, c, h, w), generator=g, device=dev) * 1.5 - 2.19 for _ in range(nbuf)]
@@ -27,7 +27,7 @@ def run(n, c, h, w, k, iters, logits, nbuf=4, smooth=False, source=None):
 
     def body():
         for b in bufs:
-            decode.decode_into(out, b, box, None, **kw)
+            decode.decode_into(out, b, box, None, _peaks_only=peaks_only, **kw)
     body()
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
@@ -50,7 +50,7 @@ def run(n, c, h, w, k, iters, logits, nbuf=4, smooth=False, source=None):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / (iters * nbuf)
     alg = n * (4 * c * h * w + 16 * k + 28 * k)
-    return dict(shape=[n, c, h, w], k=k, from_logits=logits, smooth=smooth, us=ms * 1e3, alg_GBs=alg / ms / 1e6, img_per_s=n / ms * 1e3)
+    return dict(shape=[n, c, h, w], k=k, from_logits=logits, smooth=smooth, peaks_only=peaks_only, us=ms * 1e3, alg_GBs=alg / ms / 1e6, img_per_s=n / ms * 1e3)
 
 
 if __name__ == "__main__":
@@ -69,4 +69,6 @@ if __name__ == "__main__":
     for shape in [(32, 80, 128, 128), (8, 80, 256, 256), (16, 2, 128, 128), (1, 80, 128, 128)]:
         for logits in (True, False):
             print(json.dumps(run(*shape, 100, a.iters, logits)), flush=True)
+            if shape[0] > 1:
+                print(json.dumps(run(*shape, 100, a.iters, logits, peaks_only=True)), flush=True)
     print(json.dumps(run(32, 80, 128, 128, 100, a.iters, True, smooth=True)), flush=True)
