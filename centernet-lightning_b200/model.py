@@ -246,6 +246,7 @@ class CenterNet(nn.Module):
         self.stride = bb.stride // nk.stride                                   # reference models/meta.py:96
         self.num_classes = num_classes
         self._graphs: "OrderedDict[Tuple, Any]" = OrderedDict()
+        self._stage: Dict[Tuple, List[Optional[torch.Tensor]]] = {}      # detect_host_batches: device staging buffers per shape
         self.eval()
 
     # ---- G1 names -------------------------------------------------------------------------------------------
@@ -345,10 +346,14 @@ class CenterNet(nn.Module):
         dev = device or next(self.parameters()).device
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        dev_in, ready, consumed, host_out, out_done = [None, None], [None, None], [None, None], [None, None], [None, None]
+        copy_stream.wait_stream(main)          # an abandoned earlier generator may still be reading the shared staging buffers
+        ready, consumed, host_out, out_done = [None, None], [None, None], [None, None], [None, None]
         it = iter(host_batches)
 
         def stage(slot, hb):
+            # the two device staging buffers of a shape live with the model: the captured graphs read them in place
+            # (static_input), so they must be the same tensors on every call
+            dev_in = self._stage.setdefault((tuple(hb.shape), dev.index), [None, None])
             if dev_in[slot] is None:
                 dev_in[slot] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
             with torch.cuda.stream(copy_stream):
@@ -369,7 +374,7 @@ class CenterNet(nn.Module):
             if nxt is not None:
                 stage(slot ^ 1, nxt)
             main.wait_event(ready[slot])
-            det = self.detect(dev_in[slot], static_input=True)          # the two staging buffers live as long as the generator
+            det = self.detect(self._stage[(tuple(cur.shape), dev.index)][slot], static_input=True)
             consumed[slot] = torch.cuda.Event()
             consumed[slot].record(main)
             if host_out[slot] is None:
@@ -398,22 +403,26 @@ class CenterNet(nn.Module):
         return [{k: v[i] for k, v in host.items()} for i in range(images.shape[0])]
 
     # ---- validation tail (reference models/centernet.py:202-218) ------------------------------------------------
-    evaluator = None          # any object with update(preds, targets) / get_metrics() / reset(), e.g. the reference's CocoEvaluator
+    # Any object with update(preds, targets) / get_metrics() / reset().  The reference builds CocoEvaluator(num_classes) in its
+    # constructor (models/centernet.py:115); here the pycocotools-free evaluate.CocoEvaluator is created on first use.
+    evaluator = None
 
     def validation_step(self, batch, batch_idx: int = 0):
         """``images, targets = batch``: forward + decode + xyxy->xywh on the GPU (predict_step), per-image numpy dicts,
-        targets filtered to ``boxes`` / ``labels`` and handed to ``self.evaluator.update`` exactly as the reference does.
-        The COCO evaluator itself (pycocotools) is the caller's: assign it to ``self.evaluator``."""
+        targets filtered to ``boxes`` / ``labels`` and handed to ``self.evaluator.update`` exactly as the reference does
+        (models/centernet.py:202-212)."""
         import numpy as np
         images, targets = batch
         preds = self.predict_step(images.to(next(self.parameters()).device))
         targets = [{k: np.array(t[k]) for k in ("boxes", "labels")} for t in targets]
         if self.evaluator is None:
-            raise RuntimeError("validation_step needs an evaluator: set model.evaluator (update / get_metrics / reset)")
+            from .evaluate import CocoEvaluator
+            self.evaluator = CocoEvaluator(self.num_classes)
         self.evaluator.update(preds, targets)
         return preds
 
     def validation_epoch_end(self, outputs=None) -> Dict[str, float]:
+        """reference models/centernet.py:214-218: metrics of every rank's predictions (gather_and_merge), prefixed val/."""
         metrics = self.evaluator.get_metrics()
         self.evaluator.reset()
         return {f"val/{k}": v for k, v in metrics.items()}
@@ -421,6 +430,7 @@ class CenterNet(nn.Module):
     def invalidate(self) -> None:
         """Drop every cached graph, plan and packed weight set (after changing parameters in place)."""
         self._graphs.clear()
+        self._stage.clear()
         self.model.invalidate()
 
     @torch.no_grad()

@@ -472,9 +472,17 @@ def test_validation_step_feeds_an_evaluator(cuda):
     (p, t), = net.evaluator.seen
     assert set(t[0]) == {"boxes", "labels"} and t[0]["boxes"].shape == (1, 4)
     assert net.validation_epoch_end() == {"val/n": 2.0} and net.evaluator.seen == []
+    # default evaluator = the built-in COCO evaluator (reference models/centernet.py:115); targets equal to the model's own
+    # top detections give a perfect score
+    from centernet_lightning_b200.evaluate import CocoEvaluator
     net.evaluator = None
-    with pytest.raises(RuntimeError):
-        net.validation_step((x, targets), 0)
+    own = net.predict_step(x.to(cuda))
+    own_t = [{"boxes": p["boxes"][:3], "labels": p["labels"][:3]} for p in own]
+    net.hparams.num_detections = 3
+    net.validation_step((x, own_t), 0)
+    assert isinstance(net.evaluator, CocoEvaluator)
+    out = net.validation_epoch_end()
+    assert set(out) == {f"val/{k}" for k in CocoEvaluator.metric_names} and out["val/mAP"] == pytest.approx(1.0, abs=1e-9)
 
 
 def test_resnet50_bottleneck_trunk(cuda):
