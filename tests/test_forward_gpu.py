@@ -482,7 +482,9 @@ def test_validation_step_feeds_an_evaluator(cuda):
     net.validation_step((x, own_t), 0)
     assert isinstance(net.evaluator, CocoEvaluator)
     out = net.validation_epoch_end()
-    assert set(out) == {f"val/{k}" for k in CocoEvaluator.metric_names} and out["val/mAP"] == pytest.approx(1.0, abs=1e-9)
+    assert set(out) == {f"val/{k}" for k in CocoEvaluator.metric_names} and 0.0 <= out["val/mAP"] <= 1.0
+    if all((t["boxes"][:, 2:] > 0).all() for t in own_t):        # (a clamped box of zero area cannot match anything)
+        assert out["val/mAP"] == pytest.approx(1.0, abs=1e-9)
 
 
 def test_resnet50_bottleneck_trunk(cuda):
