@@ -324,9 +324,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+          // The oldest input row (h - pad_h) is read by the r = 0 taps only: hand its slot back as soon as they are issued, so
+          // that the producer can refill it with the row the NEXT output row needs while the remaining taps still run.  A
+          // ring of kh slots then suffices and the shared memory goes to weight stages instead - the weight-tile latency
+          // (~1.2 us per 16 KB tile against ~0.2 us of MMA work per tap) is what bounds this kernel, not bandwidth.
+          if (tap == p.kw - 1) ptx::umma_commit(&a_empty_bar[first_load % p.a_slots]);
         }
-        // the oldest input row is not needed by the next output row; at the end of a strip / run none of them is
-        ptx::umma_commit(&a_empty_bar[first_load % p.a_slots]);
+        // at the end of a strip / run the other rows die as well
         if (last) for (int r = 1; r < p.kh; ++r) ptx::umma_commit(&a_empty_bar[(first_load + r) % p.a_slots]);
         ptx::umma_commit(&tmem_full_bar[as]);
       }
@@ -870,9 +874,17 @@ static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 // kernel is tensor/power-bound, not L2-bound, so halving the weight traffic changes nothing (1.229 vs 1.220 ms on the
 // 256->256 tower conv; cluster 4 strands SMs and is slower); default 1.  Each CTA loads
 // n_tile/cluster weight rows, which must stay a multiple of the 8-row swizzle atom.
-static int choose_cluster(int n_tile, int m_tiles) {
-  static const int want = [] { const char* v = getenv("CNL_CLUSTER"); int c = v ? atoi(v) : 1; return (c == 1 || c == 2 || c == 4) ? c : 1; }();
-  int c = want;
+static int cluster_env() {        // CNL_CLUSTER = 1 / 2 / 4 forces a cluster size for the single-CTA-MMA ops (0: the default rule)
+  static const int env = [] { const char* v = getenv("CNL_CLUSTER"); int c = v ? atoi(v) : 0; return (c == 1 || c == 2 || c == 4) ? c : 0; }();
+  return env;
+}
+static int choose_cluster(int n_tile, int m_tiles, int taps) {
+  const int env = cluster_env();
+  // Default: clusters of 4 for the 3x3 convs with Cout tiles of 256 on small maps (ResNet layers 3-4, the stride-16/32 FPN
+  // output convs): every CTA streams the whole 2.4-4.7 MB weight tensor per pixel tile there, and sharing each tile four
+  // ways measures 13-17 % faster (0.099 -> 0.085 ms on layer3, 0.097 -> 0.080 ms on layer4).  Everything else keeps 1:
+  // the large ops are tensor / power bound (CTA pairs), and on the 64-channel / 128-channel layers clusters only strand SMs.
+  int c = env ? env : ((n_tile == 256 && taps == 9) ? 4 : 1);
   while (c > 1 && (n_tile % (8 * c) != 0 || m_tiles < 2 * c)) c >>= 1;
   return c;
 }
@@ -950,7 +962,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   const int staging = dst.fp32_nchw ? 0 : kEpiWarps * planes * kStageWarpBytes;
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / stage_bytes);
   if (op.num_stages < 2) return fail(CNL_ERR_UNSUPPORTED, "conv tile does not fit shared memory");
-  op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
+  op.cluster = 1;                                    // decided below, after the row-rolling and CTA-pair forms
   // The separate correction accumulator pays off where the reduction is long (its rounding bias grows with the number
   // of accumulate steps); short reductions (K < 576: stem, 1x1 convs) keep the single one.
   op.corr = (op.kh * op.kw * (d.cin / 64)) >= 9;
@@ -973,7 +985,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   // shared-memory read (streamed twice instead of three times) matters more than the fill traffic
   static const bool pair128 = [] { const char* v = getenv("CNL_PAIR128"); return v && atoi(v) != 0; }();
   if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && (op.n_tile == 256 || (op.n_tile == 128 && pair128)) && !op.rows && !dst.fp32_nchw &&
-      op.cluster == 1 && e->batch * op.tiles_w * op.tiles_h >= 2 &&
+      cluster_env() <= 1 && e->batch * op.tiles_w * op.tiles_h >= 2 &&
       e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= pair_min_tiles) {     // short launches (layer3/4) measure 5-7 % slower as pairs
     op.pair = 1;
     op.cluster = 2;                                  // launch as clusters of 2; each CTA's weight box is n_tile / 2 rows
@@ -989,6 +1001,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
     op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - op.stage_depth * staging) / pair_stage);
     if (op.num_stages < 2) { op.stage_depth = 1; op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / pair_stage); }
   }
+  if (!op.pair && !op.rows) op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h, op.kh * op.kw);
 
   // pack weights: [plane][tap][cout_pad][cin], scaled by a power of two (keeps the lo parts normal in fp16)
   const int taps = op.kh * op.kw;
@@ -1029,11 +1042,19 @@ static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhw
   const int slot_bytes = (box_w * kBlockK * 2 + 1023) / 1024 * 1024;
   const int b_stage = planes * op.n_tile * kBlockK * 2;
   const int staging = kEpiWarps * planes * kStageWarpBytes;
-  int slots = op.kh + 2;                                          // two rows of look-ahead when they fit, else one
-  int b_stages = (kSmemLimit - 1024 - staging - slots * planes * slot_bytes) / b_stage;
-  if (b_stages < 3) { slots = op.kh + 1; b_stages = (kSmemLimit - 1024 - staging - slots * planes * slot_bytes) / b_stage; }
-  // fewer than three weight stages in flight and the kernel waits on weight-tile latency instead (measured on the stem's
-  // 4x1 conv: 5 row slots leave room for two stages and the im2col form is faster)
+  // Row slots: the oldest row's slot is released after the r = 0 taps (see the MMA warp), so kh slots already give the
+  // producer two thirds of an output row of look-ahead; every further slot costs weight stages, and it is the number of
+  // weight tiles in flight that hides their L2 latency.  Take the largest ring that still leaves kMinRowsStages stages
+  // (CNL_ROWS_SLOTS = slots beyond kh, for A/B timing).
+  static const int extra_env = [] { const char* v = getenv("CNL_ROWS_SLOTS"); return v ? atoi(v) : -1; }();
+  constexpr int kMinRowsStages = 5;
+  int slots = op.kh + 2, b_stages = 0;
+  for (int extra = (extra_env >= 0 ? extra_env : 2); extra >= 0; --extra) {
+    slots = op.kh + extra;
+    b_stages = (kSmemLimit - 1024 - staging - slots * planes * slot_bytes) / b_stage;
+    if (b_stages >= kMinRowsStages || extra_env >= 0) break;
+  }
+  // fewer than three weight stages in flight and the kernel waits on weight-tile latency instead
   if (b_stages < 3 || slots > kMaxStages) return false;
   op.rows = 1; op.a_slots = slots; op.a_slot_bytes = slot_bytes; op.box_w = box_w;
   op.num_stages = std::min(kMaxStages, b_stages);
@@ -1060,13 +1081,14 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   const int planes = e->planes;
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - kEpiWarps * planes * kStageWarpBytes) / stage_bytes);
-  op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h);
+  op.cluster = 1;
   op.cat = (e->precision == CNL_PRECISION_SPLIT) && cat_enabled();
   op.corr = op.cat;                        // K = 256: the correction accumulator only comes with the cat MMA
   op.corr_off = op.cat ? 64 : 128; op.acc_stages = 2;
   op.pair = 0;
   op.stage_depth = 1;
   plan_rows_mode(op, planes, 64, 1, true, e->precision);
+  if (!op.rows) op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h, 4);
   // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
@@ -1157,7 +1179,8 @@ size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer) {
 int cnl_engine_op_form(const cnl_engine* e, int op) {
   if (!e || op < 0 || op >= (int)e->ops.size()) return -1;
   const OpInfo& o = e->ops[op];
-  return (o.rows ? 1 : 0) | (o.pair ? 2 : 0) | (o.corr ? 4 : 0) | (o.cat ? 8 : 0);
+  return (o.rows ? 1 : 0) | (o.pair ? 2 : 0) | (o.corr ? 4 : 0) | (o.cat ? 8 : 0) | (o.cluster << 4) | (o.num_stages << 8) | (o.stage_depth << 12) |
+         (o.a_slots << 16) | ((o.n_tile / 16) << 20);
 }
 
 int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {

@@ -191,7 +191,9 @@ size_t cnl_engine_arena_bytes(const cnl_engine* e);
 size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer);
 
 /* Kernel form the plan chose for op `op` (for tests and profiles): bit 0 = row-rolling A operand, bit 1 = CTA pair
- * (cta_group::2), bit 2 = separate correction accumulator, bit 3 = concatenated hi*[hi|lo] MMA; -1 for a bad index. */
+ * (cta_group::2), bit 2 = separate correction accumulator, bit 3 = concatenated hi*[hi|lo] MMA, bits 4-7 = CTAs per cluster,
+ * bits 8-11 = load stages, bits 12-15 = epilogue staging depth, bits 16-19 = input-row slots, bits 20-27 = Cout tile / 16;
+ * -1 for a bad index. */
 int cnl_engine_op_form(const cnl_engine* e, int op);
 
 /* Upload packed weights into the arena (once, or again after a weight change). */
