@@ -26,7 +26,9 @@ class ConvDesc(C.Structure):
                 ("src_c_off", C.c_int), ("dst_c_off", C.c_int), ("residual", C.c_int), ("residual_up", C.c_int),
                 ("kh", C.c_int), ("kw", C.c_int), ("pad_h", C.c_int), ("pad_w", C.c_int),
                 ("dst_up", C.c_int), ("dst_phase", C.c_int),
-                ("weight_host", C.c_void_p), ("bias_host", C.c_void_p)]
+                ("weight_host", C.c_void_p), ("bias_host", C.c_void_p),
+                ("src2", C.c_int), ("src3", C.c_int), ("scale0", C.c_float), ("scale1", C.c_float), ("scale2", C.c_float),
+                ("resize", C.c_int)]
 
 
 class BufferDesc(C.Structure):

@@ -523,6 +523,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            if (p.relu == 2) {                             // ReLU6 (separable convs, MobileNetV2)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fminf(v[j], 6.0f);
+            }
           }
           // The TMA unit serves this warp's small stores behind the producer's 64-96 KB loads, so a store takes ~1 us to
           // finish reading its staging buffer; with ONE buffer per warp every chunk waited for the previous chunk's store
@@ -614,6 +618,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             if (valid && c < p.cout_real) {
               float val = fmaf(v[j], p.wscale_inv, __ldg(p.bias + c));
               if (p.relu) val = fmaxf(val, 0.0f);
+              if (p.relu == 2) val = fminf(val, 6.0f);
               if (p.sigmoid) val = sigmoid32(val);         // the kernel is HBM-bound: the logistic hides behind the loads
               out_px[c * cstride] = val;
             }
@@ -770,6 +775,172 @@ pool_planes_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
   if (NPLANE == 2) *reinterpret_cast<uint4*>(out + out_plane + o) = lo;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Bandwidth-bound ops of the separable-conv models (reference models/layers.py:40-79 `make_conv` separable branch,
+// :138-177 `Fuse`; MobileNetV2's depthwise stages).  CUDA-core kernels on the same NHWC hi/lo planes: one thread = one
+// output pixel x 8 channels (one 16-byte vector per plane), fp32 arithmetic on value = hi + lo.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const __half* p, long long plane, bool two, float (&f)[8]) {
+  const uint4 uh = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const float2 a = __half22float2(hh[q]); f[2 * q] = a.x; f[2 * q + 1] = a.y; }
+  if (two) {
+    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(p + plane));
+    const __half2* ll = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 a = __half22float2(ll[q]); f[2 * q] += a.x; f[2 * q + 1] += a.y; }
+  }
+}
+__device__ __forceinline__ void store8(__half* p, long long plane, bool two, const float (&m)[8]) {
+  uint4 hi, lo;
+  __half2* hh = reinterpret_cast<__half2*>(&hi);
+  __half2* ll = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 h2 = __floats2half2_rn(m[2 * j], m[2 * j + 1]);
+    hh[j] = h2;
+    const float2 back = __half22float2(h2);
+    ll[j] = __floats2half2_rn(m[2 * j] - back.x, m[2 * j + 1] - back.y);
+  }
+  *reinterpret_cast<uint4*>(p) = hi;
+  if (two) *reinterpret_cast<uint4*>(p + plane) = lo;
+}
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act) v = fmaxf(v, 0.0f);
+  if (act == 2) v = fminf(v, 6.0f);
+  return v;
+}
+
+// depthwise 3x3, pad 1, stride 1 or 2: out[n,y,x,c] = act(bias[c] + sum_{r,s} w[r*3+s][c] * in[n, y*stride+r-1, x*stride+s-1, c])
+// (taps accumulated in the order r, s - the order ATen's direct depthwise kernel uses; fp32 FMAs)
+template <int NPLANE>
+__global__ void __launch_bounds__(256)
+dw3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, const float* __restrict__ w9c, const float* __restrict__ bias,
+             int N, int IH, int IW, int C, int stride, int act, long long in_plane, long long out_plane) {
+  const int OH = IH / stride, OW = IW / stride, C8 = C / 8;
+  const long long total = (long long)N * OH * OW * C8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c8 = (int)(t % C8);
+  long long pix = t / C8;
+  const int ox = (int)(pix % OW);
+  pix /= OW;
+  const int oy = (int)(pix % OH);
+  const int n = (int)(pix / OH);
+  float acc[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int y = oy * stride + r - 1;
+    if (y < 0 || y >= IH) continue;
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx) {
+      const int x = ox * stride + sx - 1;
+      if (x < 0 || x >= IW) continue;
+      float f[8];
+      load8(in + (((size_t)n * IH + y) * IW + x) * C + c8 * 8, in_plane, NPLANE == 2, f);
+      const float* wp = w9c + (size_t)(r * 3 + sx) * C + c8 * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]); acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]); acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = act_apply(acc[j], act);
+  store8(out + (((size_t)n * OH + oy) * OW + ox) * C + c8 * 8, out_plane, NPLANE == 2, acc);
+}
+
+// Fuse node (reference models/layers.py:160-176): out = sum_i scale_i * x_i over up to three maps; the LAST one is resized
+// first: resize 1 = nearest x2 up-sample (it has half the output resolution), 2 = MaxPool2d(2, 2) (twice the resolution).
+template <int NPLANE>
+__global__ void __launch_bounds__(256)
+fuse_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ c, __half* __restrict__ out,
+            float sa, float sb, float sc, int n_src, int resize, int N, int H, int W, int C, long long plane, long long last_plane) {
+  const int C8 = C / 8;
+  const long long total = (long long)N * H * W * C8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c8 = (int)(t % C8);
+  long long pix = t / C8;
+  const int x = (int)(pix % W);
+  pix /= W;
+  const int y = (int)(pix % H);
+  const int n = (int)(pix / H);
+  const size_t o = (((size_t)n * H + y) * W + x) * C + c8 * 8;
+  const __half* srcs[3] = {a, b, c};
+  const float scales[3] = {sa, sb, sc};
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  for (int i = 0; i < n_src; ++i) {
+    float f[8];
+    if (i < n_src - 1 || resize == 0) {
+      load8(srcs[i] + o, plane, NPLANE == 2, f);
+    } else if (resize == 1) {
+      const int LH = H / 2, LW = W / 2;
+      load8(srcs[i] + (((size_t)n * LH + (y >> 1)) * LW + (x >> 1)) * C + c8 * 8, last_plane, NPLANE == 2, f);
+    } else {
+      const int LH = H * 2, LW = W * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = -INFINITY;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          float g[8];
+          load8(srcs[i] + (((size_t)n * LH + (2 * y + dy)) * LW + (2 * x + dx)) * C + c8 * 8, last_plane, NPLANE == 2, g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], g[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], scales[i], acc[j]);
+  }
+  store8(out + o, plane, NPLANE == 2, acc);
+}
+
+// MobileNetV2 stem: conv3x3 stride 2 pad 1 from the fp32 NCHW image (3 channels) + bias + activation -> NHWC planes with C
+// (padded) channels.  w27c: [(c*3 + r)*3 + s][C] fp32.  One thread = one output pixel x 8 output channels.
+template <int NPLANE>
+__global__ void __launch_bounds__(256)
+stem3x3_kernel(const float* __restrict__ image, __half* __restrict__ out, const float* __restrict__ w27c, const float* __restrict__ bias,
+               int N, int H, int W, int C, int act, long long out_plane) {
+  const int OH = H / 2, OW = W / 2, C8 = C / 8;
+  const long long total = (long long)N * OH * OW * C8;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c8 = (int)(t % C8);
+  long long pix = t / C8;
+  const int ox = (int)(pix % OW);
+  pix /= OW;
+  const int oy = (int)(pix % OH);
+  const int n = (int)(pix / OH);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + c8 * 8 + j);
+  for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int y = 2 * oy + r - 1;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const int x = 2 * ox + sx - 1;
+        if (x < 0 || x >= W) continue;
+        const float v = __ldg(image + (((size_t)n * 3 + ch) * H + y) * W + x);
+        const float* wp = w27c + (size_t)((ch * 3 + r) * 3 + sx) * C + c8 * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, __ldg(wp + j), acc[j]);
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = act_apply(acc[j], act);
+  store8(out + (((size_t)n * OH + oy) * OW + ox) * C + c8 * 8, out_plane, NPLANE == 2, acc);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Layout converters (tests / debugging): NHWC fp16 planes <-> NCHW fp32
 // ------------------------------------------------------------------------------------------------------------
@@ -826,6 +997,7 @@ struct OpInfo {
   size_t w_offset, bias_offset, scratch_offset;
   std::vector<__half> w_packed;       // [plane][tap][cout_pad][cin]
   std::vector<float> bias_packed;     // [cout_pad]   (stem: [64]);
+  std::vector<float> w_f32;           // kinds 2 / 4 (depthwise 3x3, 3x3/2 image stem): [tap][C] fp32
   size_t stem_t_offset, stem_s_offset;   // stem scratch: im2row tensor T and the un-pooled conv output S
   CUtensorMap src_map, w_map, dst_map;
 };
@@ -936,7 +1108,11 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   if (env_ntile == 128 && d.cout % 128 == 0 && d.cout > 128 && !dst.fp32_nchw) { op.n_tile = 128; op.cout_pad = d.cout; }   // experiment
   else if (d.cout % 256 == 0) { op.n_tile = 256; op.cout_pad = d.cout; }
   else if (d.cout <= 256) { op.cout_pad = (d.cout + 15) / 16 * 16; op.n_tile = op.cout_pad; }
-  else return fail(CNL_ERR_UNSUPPORTED, "conv Cout=%d (must be <= 256 or a multiple of 256)", d.cout);
+  // wider layers that are not multiples of 256 (MobileNetV2's 384 / 576 / 960 / 320 channels): the widest of 192 / 128 / 64 that divides
+  else if (d.cout % 192 == 0) { op.n_tile = 192; op.cout_pad = d.cout; }
+  else if (d.cout % 128 == 0) { op.n_tile = 128; op.cout_pad = d.cout; }
+  else if (d.cout % 64 == 0) { op.n_tile = 64; op.cout_pad = d.cout; }
+  else return fail(CNL_ERR_UNSUPPORTED, "conv Cout=%d (must be <= 256 or a multiple of 64)", d.cout);
   op.n_tiles = op.cout_pad / op.n_tile;
   if (!dst.fp32_nchw) {
     if (d.cout % 64 || d.dst_c_off % 64) return fail(CNL_ERR_UNSUPPORTED, "NHWC conv output needs Cout %% 64 == 0");
@@ -1061,6 +1237,54 @@ static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhw
   return true;
 }
 
+
+// kinds 2 (depthwise 3x3), 3 (fuse), 4 (3x3/2 stem from the image): CUDA-core kernels on the NHWC planes
+static int prepare_elementwise(cnl_engine* e, OpInfo& op) {
+  const cnl_conv_desc& d = op.d;
+  const BufferInfo& dst = e->bufs[d.dst];
+  op.rows = 0; op.pair = 0; op.corr = false; op.cat = 0; op.cluster = 1; op.num_stages = 0; op.stage_depth = 0; op.a_slots = 0; op.n_tile = 0;
+  op.wscale = 1.0f; op.up = 1; op.kh = op.kw = 3; op.pad_h = op.pad_w = 1; op.acc_stages = 0; op.corr_off = 0; op.tw = op.th = 0; op.tiles_w = op.tiles_h = 0;
+  op.store_w = op.store_h = 0; op.n_tiles = 0; op.cout_pad = 0; op.a_slot_bytes = 0; op.box_w = 0;
+  if (dst.fp32_nchw || dst.channels % 8) return fail(CNL_ERR_UNSUPPORTED, "depthwise / fuse / stem3x3 ops write NHWC buffers with C %% 8 == 0");
+  if (d.kind == 2) {
+    const BufferInfo& src = e->bufs[d.src];
+    if (src.fp32_nchw || src.channels != dst.channels || d.cin != dst.channels || d.cout != dst.channels || d.ksize != 3 || d.pad != 1 ||
+        (d.stride != 1 && d.stride != 2) || src.h / d.stride != dst.h || src.w / d.stride != dst.w || d.residual >= 0)
+      return fail(CNL_ERR_UNSUPPORTED, "depthwise op: 3x3, pad 1, stride 1 or 2, same channel count on both sides, no residual");
+    const int C = dst.channels;
+    op.w_f32.assign((size_t)9 * C, 0.f);
+    for (int c = 0; c < C; ++c)
+      for (int t = 0; t < 9; ++t) op.w_f32[(size_t)t * C + c] = d.weight_host[(size_t)c * 9 + t];
+    op.bias_packed.assign(d.bias_host, d.bias_host + C);
+    return CNL_OK;
+  }
+  if (d.kind == 3) {
+    const int srcs[3] = {d.src, d.src2, d.src3};
+    const int n_src = d.src3 >= 0 ? 3 : 2;
+    if (d.src2 < 0 || d.src2 >= (int)e->bufs.size() || d.src3 >= (int)e->bufs.size()) return fail(CNL_ERR_INVALID_ARGUMENT, "fuse op: bad source buffer id");
+    if (d.resize < 0 || d.resize > 2) return fail(CNL_ERR_INVALID_ARGUMENT, "fuse op: resize %d", d.resize);
+    for (int i = 0; i < n_src; ++i) {
+      const BufferInfo& sb = e->bufs[srcs[i]];
+      const bool last = i == n_src - 1;
+      const int eh = last && d.resize == 1 ? dst.h / 2 : (last && d.resize == 2 ? dst.h * 2 : dst.h);
+      const int ew = last && d.resize == 1 ? dst.w / 2 : (last && d.resize == 2 ? dst.w * 2 : dst.w);
+      if (sb.fp32_nchw || sb.channels != dst.channels || sb.h != eh || sb.w != ew) return fail(CNL_ERR_INVALID_ARGUMENT, "fuse op: source %d shape mismatch", i);
+    }
+    return CNL_OK;
+  }
+  // kind 4
+  const BufferInfo& src = e->bufs[d.src];
+  if (!src.fp32_nchw || src.channels != 3 || d.cin != 3 || d.ksize != 3 || d.stride != 2 || d.pad != 1 || d.cout != dst.channels ||
+      dst.h * 2 != src.h || dst.w * 2 != src.w)
+    return fail(CNL_ERR_UNSUPPORTED, "stem3x3 must be conv3x3/2 pad 1 from the fp32 image");
+  const int C = dst.channels;
+  op.w_f32.assign((size_t)27 * C, 0.f);
+  for (int c = 0; c < C; ++c)
+    for (int t = 0; t < 27; ++t) op.w_f32[(size_t)t * C + c] = d.weight_host[(size_t)c * 27 + t];
+  op.bias_packed.assign(d.bias_host, d.bias_host + C);
+  return CNL_OK;
+}
+
 static int prepare_stem(cnl_engine* e, OpInfo& op) {
   const cnl_conv_desc& d = op.d;
   const BufferInfo& src = e->bufs[d.src];
@@ -1145,7 +1369,8 @@ int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_bu
     if (op.d.src < 0 || op.d.src >= n_buffers || op.d.dst <= 0 || op.d.dst >= n_buffers || op.d.residual >= n_buffers) {
       delete e; return fail(CNL_ERR_INVALID_ARGUMENT, "op %d: bad buffer id", i);
     }
-    int st = (op.d.kind == 1) ? prepare_stem(e, op) : prepare_conv(e, op);
+    if (op.d.kind < 0 || op.d.kind > 4) { delete e; return fail(CNL_ERR_INVALID_ARGUMENT, "op %d: kind %d", i, op.d.kind); }
+    int st = (op.d.kind == 1) ? prepare_stem(e, op) : (op.d.kind >= 2 ? prepare_elementwise(e, op) : prepare_conv(e, op));
     if (st != CNL_OK) { delete e; return st; }
     op.d.weight_host = nullptr; op.d.bias_host = nullptr;
     if (op.d.kind == 1) {
@@ -1154,6 +1379,10 @@ int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_bu
       op.bias_offset = off; off += align_up(64 * 4, 1024);
       op.stem_t_offset = off; off += align_up(half_res, 1024);
       op.stem_s_offset = off; off += align_up(half_res, 1024);
+      op.scratch_offset = 0;
+    } else if (op.d.kind >= 2) {
+      op.w_offset = off; off += align_up(op.w_f32.size() * 4 + 16, 1024);
+      op.bias_offset = off; off += align_up(op.bias_packed.size() * 4 + 16, 1024);
       op.scratch_offset = 0;
     } else {
       op.w_offset = off; off += align_up(op.w_packed.size() * 2, 1024);
@@ -1179,6 +1408,7 @@ size_t cnl_engine_buffer_offset(const cnl_engine* e, int buffer) {
 int cnl_engine_op_form(const cnl_engine* e, int op) {
   if (!e || op < 0 || op >= (int)e->ops.size()) return -1;
   const OpInfo& o = e->ops[op];
+  if (o.d.kind >= 2) return 0;                       // CUDA-core op (depthwise / fuse / stem3x3)
   return (o.rows ? 1 : 0) | (o.pair ? 2 : 0) | (o.corr ? 4 : 0) | (o.cat ? 8 : 0) | (o.cluster << 4) | (o.num_stages << 8) | (o.stage_depth << 12) |
          (o.a_slots << 16) | ((o.n_tile / 16) << 20);
 }
@@ -1221,6 +1451,11 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       cuuint32_t we[3] = {1, 1, 1};
       r = encode_map(&op.w_map, base + op.w_offset, 3, wd, ws, wb, we, "stem weights");
       if (r) return r;
+      continue;
+    }
+    if (d.kind >= 2) {
+      if (!op.w_f32.empty()) CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_f32.data(), op.w_f32.size() * 4, cudaMemcpyHostToDevice, st));
+      if (!op.bias_packed.empty()) CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.bias_offset, op.bias_packed.data(), op.bias_packed.size() * 4, cudaMemcpyHostToDevice, st));
       continue;
     }
     CNL_CUDA_CHECK(cudaMemcpyAsync(base + op.w_offset, op.w_packed.data(), op.w_packed.size() * 2, cudaMemcpyHostToDevice, st));
@@ -1348,6 +1583,33 @@ int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int f
       if (planes == 2) pool_planes_kernel<2><<<b2, 256, 0, st>>>(S, o, e->batch, SH, SW, half_plane, dst.plane_elems);
       else             pool_planes_kernel<1><<<b2, 256, 0, st>>>(S, o, e->batch, SH, SW, half_plane, dst.plane_elems);
       n_launch += 3;
+      CNL_CUDA_CHECK(cudaGetLastError());
+      continue;
+    }
+    if (d.kind >= 2) {
+      const long long total = (long long)e->batch * dst.h * dst.w * (dst.channels / 8);
+      const int blocks = (int)((total + 255) / 256);
+      __half* o = reinterpret_cast<__half*>(base + dst.offset);
+      const float* wf = reinterpret_cast<const float*>(base + op.w_offset);
+      if (d.kind == 2) {
+        const BufferInfo& src = e->bufs[d.src];
+        const __half* in = reinterpret_cast<const __half*>(base + src.offset);
+        if (planes == 2) dw3x3_kernel<2><<<blocks, 256, 0, st>>>(in, o, wf, p.bias, e->batch, src.h, src.w, dst.channels, d.stride, d.relu, src.plane_elems, dst.plane_elems);
+        else             dw3x3_kernel<1><<<blocks, 256, 0, st>>>(in, o, wf, p.bias, e->batch, src.h, src.w, dst.channels, d.stride, d.relu, src.plane_elems, dst.plane_elems);
+      } else if (d.kind == 3) {
+        const int n_src = d.src3 >= 0 ? 3 : 2;
+        const int last = n_src == 3 ? d.src3 : d.src2;
+        const __half* a = reinterpret_cast<const __half*>(base + e->bufs[d.src].offset);
+        const __half* b = reinterpret_cast<const __half*>(base + e->bufs[d.src2].offset);
+        const __half* c = d.src3 >= 0 ? reinterpret_cast<const __half*>(base + e->bufs[d.src3].offset) : nullptr;
+        if (planes == 2) fuse_kernel<2><<<blocks, 256, 0, st>>>(a, b, c, o, d.scale0, d.scale1, d.scale2, n_src, d.resize, e->batch, dst.h, dst.w, dst.channels, dst.plane_elems, e->bufs[last].plane_elems);
+        else             fuse_kernel<1><<<blocks, 256, 0, st>>>(a, b, c, o, d.scale0, d.scale1, d.scale2, n_src, d.resize, e->batch, dst.h, dst.w, dst.channels, dst.plane_elems, e->bufs[last].plane_elems);
+      } else {
+        if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
+        if (planes == 2) stem3x3_kernel<2><<<blocks, 256, 0, st>>>(image, o, wf, p.bias, e->batch, e->height, e->width, dst.channels, d.relu, dst.plane_elems);
+        else             stem3x3_kernel<1><<<blocks, 256, 0, st>>>(image, o, wf, p.bias, e->batch, e->height, e->width, dst.channels, d.relu, dst.plane_elems);
+      }
+      ++n_launch;
       CNL_CUDA_CHECK(cudaGetLastError());
       continue;
     }

@@ -17,6 +17,7 @@ from . import _lib
 from .plan import Plan
 
 PRECISION_SPLIT = 0   # fp16 hi+lo operands, 3 tensor-core passes, fp32 accumulate: fp32-equivalent (parity default)
+_KINDS = {"conv": 0, "stem": 1, "dw": 2, "fuse": 3, "stem3x3": 4}     # cnl_conv_desc.kind (include/cnl_b200.h)
 PRECISION_FAST = 1    # single fp16 pass: ~1e-1 logit error on a 50-conv network, reported separately
 
 
@@ -42,12 +43,14 @@ class Engine:
             w = np.ascontiguousarray(op.weight.detach().cpu().numpy(), dtype=np.float32)
             b = np.ascontiguousarray(op.bias.detach().cpu().numpy(), dtype=np.float32)
             self._keep += [w, b]
+            srcs = [self.buffer_ids[s] for s in (op.srcs or [])] + [-1, -1, -1]
+            scales = list(op.scales or []) + [0.0, 0.0, 0.0]
             ops[i] = _lib.ConvDesc(
-                1 if op.kind == "stem" else 0, self.buffer_ids[op.src], self.buffer_ids[op.dst], op.cin, op.cout,
+                _KINDS[op.kind], self.buffer_ids[op.src], self.buffer_ids[op.dst], op.cin, op.cout,
                 op.ksize, op.stride, op.pad, int(op.relu), op.src_c_off, op.dst_c_off,
                 self.buffer_ids[op.residual] if op.residual is not None else -1, op.residual_up,
                 op.kh, op.kw, op.pad_h, op.pad_w, op.dst_up, op.dst_phase,
-                w.ctypes.data, b.ctypes.data)
+                w.ctypes.data, b.ctypes.data, srcs[1], srcs[2], scales[0], scales[1], scales[2], op.resize)
         handle = C.c_void_p()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         st = self.lib.cnl_engine_create(C.byref(handle), bufs, len(plan.buffers), ops, len(plan.ops),

@@ -33,7 +33,7 @@ from torch import nn
 from . import decode as _decode
 from . import _lib
 from .engine import Engine, PRECISION_FAST, PRECISION_SPLIT
-from .plan import RESNET_DEPTHS, RESNET_WIDTHS, build_plan, resnet_out_channels
+from .plan import MOBILENET_V2_STRIDES, RESNET_DEPTHS, RESNET_WIDTHS, backbone_out_channels, build_plan, resnet_out_channels
 
 _PRECISIONS = {"split": PRECISION_SPLIT, "fp32": PRECISION_SPLIT, "split_fused": 2, "fast": PRECISION_FAST, "fp16": PRECISION_FAST}
 
@@ -73,13 +73,49 @@ class _Bottleneck(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
 
 
+class _InvertedResidual(nn.Module):
+    """Parameter layout of torchvision's mobilenet_v2 InvertedResidual (``conv.<i>...`` keys)."""
+
+    def __init__(self, cin, cout, stride, expand):
+        super().__init__()
+        hid = cin * expand
+        layers = []
+        if expand != 1:
+            layers.append(nn.Sequential(nn.Conv2d(cin, hid, 1, bias=False), nn.BatchNorm2d(hid)))
+        layers += [nn.Sequential(nn.Conv2d(hid, hid, 3, stride, 1, groups=hid, bias=False), nn.BatchNorm2d(hid)),
+                   nn.Conv2d(hid, cout, 1, bias=False), nn.BatchNorm2d(cout)]
+        self.conv = nn.Sequential(*layers)
+        self.use_res_connect = stride == 1 and cin == cout
+
+
+class _MobileNetV2(nn.Module):
+    """torchvision mobilenet_v2 ``features[0:18]`` parameter tree (one of the backbones the reference's tests name,
+    tests/test_models.py:37); features at strides 4 / 8 / 16 / 32 = outputs of features[3], [6], [13], [17]."""
+    stride = 32
+    name = "mobilenet_v2"
+
+    def __init__(self):
+        super().__init__()
+        feats = [nn.Sequential(nn.Conv2d(3, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32))]
+        cin = 32
+        for t, c, n, s_ in ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)):
+            for i in range(n):
+                feats.append(_InvertedResidual(cin, c, s_ if i == 0 else 1, t))
+                cin = c
+        self.features = nn.Sequential(*feats)
+        assert all(MOBILENET_V2_STRIDES[i] == f.conv[-3][0].stride[0] for i, f in enumerate(self.features) if i > 0)
+
+    def get_out_channels(self):
+        return list(backbone_out_channels("mobilenet_v2"))
+
+
 class _Backbone(nn.Module):
     stride = 32
 
     def __init__(self, name):
         super().__init__()
         if name not in RESNET_DEPTHS:
-            raise ValueError(f"backbone {name!r}: the sm_100a engine implements {sorted(RESNET_DEPTHS)}")
+            raise ValueError(f"backbone {name!r}: the sm_100a engine implements {sorted(RESNET_DEPTHS) + ['mobilenet_v2']}")
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
@@ -139,6 +175,70 @@ class _SimpleNeck(nn.Module):
 
     def get_out_channels(self):
         return self.out_channels
+
+
+def _make_conv(cin, cout, conv_type):
+    """Parameter layout of the reference's make_conv (models/layers.py:40-79): Sequential indices 0,1 (normal) or 0,1,3,4
+    (separable: depthwise 3x3 + BN, pointwise 1x1 + BN; index 2 / 5 are the parameter-free activations)."""
+    if conv_type == "separable":
+        return nn.Sequential(nn.Conv2d(cin, cin, 3, padding=1, groups=cin, bias=False), nn.BatchNorm2d(cin), nn.Identity(),
+                             nn.Conv2d(cin, cout, 1, bias=False), nn.BatchNorm2d(cout))
+    if conv_type != "normal":
+        raise ValueError(f"conv_type {conv_type!r}: 'normal' and 'separable' are lowered (deformable convs are not)")
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout))
+
+
+class _Fuse(nn.Module):
+    """Parameter layout of the reference's Fuse node (models/layers.py:138-177): project.<i> (1x1 conv with bias where the
+    channel count differs), weights (weighted fusion), output_conv (make_conv)."""
+
+    def __init__(self, in_channels, out, conv_type="normal", weighted_fusion=False):
+        super().__init__()
+        self.project = nn.ModuleList([nn.Conv2d(c, out, 1) if c != out else None for c in in_channels])
+        self.weights = nn.Parameter(torch.ones(len(in_channels))) if weighted_fusion else None
+        self.output_conv = _make_conv(out, out, conv_type)
+
+
+class _IDANeck(nn.Module):
+    """IDANeck (reference docs/implementation.md:43; class absent from the snapshot, reconstructed from its Fuse node):
+    consecutive maps are fused pairwise, level after level, until one stride-4 map with in_channels[0] channels is left."""
+
+    def __init__(self, in_channels, conv_type="normal", weighted_fusion=False):
+        super().__init__()
+        self.stride = 2 ** (len(in_channels) - 1)
+        self.out_channels = in_channels[0]
+        self.levels = nn.ModuleList()
+        chans = list(in_channels)
+        while len(chans) > 1:
+            self.levels.append(nn.ModuleList([_Fuse([chans[i], chans[i + 1]], chans[i], conv_type, weighted_fusion)
+                                              for i in range(len(chans) - 1)]))
+            chans = chans[:-1]
+
+    def get_out_channels(self):
+        return self.out_channels
+
+
+class _BiFPNNeck(nn.Module):
+    """BiFPNNeck (reference docs/implementation.md:42; reconstructed from the Fuse node): 1x1 projections to ``out_channels``,
+    then ``num_layers`` x (top-down Fuse "up" pass, bottom-up Fuse "down" pass); the stride-4 map is returned."""
+
+    def __init__(self, in_channels, out_channels=64, num_layers=2, conv_type="normal", weighted_fusion=True):
+        super().__init__()
+        n, d = len(in_channels), out_channels
+        self.stride = 2 ** (n - 1)
+        self.out_channels = d
+        self.project = nn.ModuleList([nn.Conv2d(c, d, 1) for c in in_channels])
+        self.top_down = nn.ModuleList([nn.ModuleList([_Fuse([d, d], d, conv_type, weighted_fusion) for _ in range(n - 1)])
+                                       for _ in range(num_layers)])
+        self.bottom_up = nn.ModuleList([nn.ModuleList([_Fuse([d, d, d] if i < n - 2 else [d, d], d, conv_type, weighted_fusion)
+                                                       for i in range(n - 1)]) for _ in range(num_layers)])
+
+    def get_out_channels(self):
+        return self.out_channels
+
+
+_NECKS = {"FPN": "FPN", "fpn": "FPN", "FPNNeck": "FPN", "simple": "simple", "SimpleNeck": "simple", "ida": "ida", "IDANeck": "ida",
+          "bifpn": "bifpn", "BiFPNNeck": "bifpn"}
 
 
 class _Head(nn.Module):
@@ -224,8 +324,9 @@ class CenterNet(nn.Module):
         super().__init__()
         if pretrained_backbone:
             raise RuntimeError("pretrained_backbone=True needs a download; load weights with load_state_dict() instead")
-        if neck not in ("FPN", "simple", "SimpleNeck"):
-            raise ValueError(f"neck {neck!r}: the sm_100a engine lowers the FPN and simple necks (SURVEY 8a F2, 8f rank 4)")
+        if neck not in _NECKS:
+            raise ValueError(f"neck {neck!r}: the sm_100a engine lowers {sorted(set(_NECKS.values()))} (SURVEY 8a F2, 8f rank 4)")
+        neck = _NECKS[neck]
         if nms_kernel % 2 != 1:
             raise ValueError("nms_kernel must be odd")
         neck_config = dict(neck_config or {})
@@ -234,8 +335,8 @@ class CenterNet(nn.Module):
                                        head_config=head_config, box_log=box_log, box_multiplier=box_multiplier,
                                        heatmap_prior=heatmap_prior, nms_kernel=nms_kernel, num_detections=num_detections,
                                        reid_dim=reid_dim, precision=precision, **training_only)
-        bb = _Backbone(backbone)
-        nk = _FPN(bb.get_out_channels(), **neck_config) if neck == "FPN" else _SimpleNeck(bb.get_out_channels(), **neck_config)
+        bb = _MobileNetV2() if backbone == "mobilenet_v2" else _Backbone(backbone)
+        nk = {"FPN": _FPN, "simple": _SimpleNeck, "ida": _IDANeck, "bifpn": _BiFPNNeck}[neck](bb.get_out_channels(), **neck_config)
         heads = nn.Module()
         c = nk.get_out_channels()
         heads.add_module("heatmap", _Head(c, num_classes, init_bias=math.log(heatmap_prior / (1 - heatmap_prior)), **head_config))
@@ -441,7 +542,7 @@ class CenterNet(nn.Module):
         g = torch.Generator().manual_seed(seed)
         for name, mod in self.model.named_modules():
             if isinstance(mod, nn.Conv2d):
-                fan_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1]
+                fan_in = mod.in_channels // mod.groups * mod.kernel_size[0] * mod.kernel_size[1]
                 mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
                 if name.endswith("out_conv"):
                     mod.weight.mul_(0.2)             # head logits with std ~1.5 around the prior, like a trained heatmap

@@ -155,11 +155,16 @@ enum { CNL_PRECISION_SPLIT = 0, CNL_PRECISION_FAST = 1, CNL_PRECISION_SPLIT_FUSE
 
 /* One fused convolution: out = act(conv(in, w) + bias [+ residual]).  Host-side description. */
 typedef struct {
-  int kind;            /* 0 = conv (tcgen05 implicit GEMM), 1 = stem (7x7/2 conv + ReLU + 3x3/2 max-pool) */
+  int kind;            /* 0 = conv (tcgen05 implicit GEMM), 1 = stem (7x7/2 conv + ReLU + 3x3/2 max-pool),
+                          2 = depthwise 3x3 conv, pad 1, stride 1/2 (reference models/layers.py:58-62 and
+                              MobileNetV2's depthwise stages; weight (C,1,3,3)),
+                          3 = fusion node: dst = scale0*src + scale1*src2 [+ scale2*src3], the last source
+                              resized first (reference models/layers.py:138-177 `Fuse`),
+                          4 = 3x3/2 conv from the fp32 image (MobileNetV2 stem; weight (cout,3,3,3))          */
   int src, dst;        /* buffer ids                                                                      */
   int cin, cout;       /* real channel counts                                                             */
   int ksize, stride, pad;
-  int relu;
+  int relu;            /* 0 = linear, 1 = ReLU, 2 = ReLU6 (reference models/layers.py:60,64)                             */
   int src_c_off, dst_c_off;
   int residual;        /* buffer id or -1                                                                 */
   int residual_up;     /* 1 or 2 (nearest-upsampled half-resolution residual)                             */
@@ -172,6 +177,10 @@ typedef struct {
                           ConvTranspose2d (reference models/layers.py:86-96)                              */
   const float* weight_host;   /* (cout, cin, kh, kw) fp32, BatchNorm already folded                       */
   const float* bias_host;     /* (cout,) fp32                                                             */
+  /* kind 3 only */
+  int src2, src3;             /* further source buffers (src3 = -1: two inputs)                           */
+  float scale0, scale1, scale2;
+  int resize;                 /* of the LAST source: 0 = none, 1 = nearest x2 up-sample, 2 = MaxPool2d(2,2) */
 } cnl_conv_desc;
 
 typedef struct {

@@ -63,6 +63,14 @@ def import_reference():
     return cn, meta
 
 
+def import_reference_layers():
+    """The reference's own ``centernet_lightning.models.layers`` (make_conv :40-79, make_upsample :81-99, Fuse :138-177);
+    it only needs torch + torchvision.ops.DeformConv2d, both installed."""
+    import_reference()
+    import importlib
+    return importlib.import_module("centernet_lightning.models.layers")
+
+
 def reference_decode(heatmap, box_offsets, *, num_detections=100, nms_kernel=3, normalize_boxes=False,
                      box_log=False, box_multiplier=1.0, stride=4):
     """Run the reference's own CenterNet.decode_detections (models/centernet.py:229-241) unbound,

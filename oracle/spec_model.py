@@ -139,6 +139,142 @@ class ResNetTrunk(nn.Module):
         return outs
 
 
+class MobileNetV2Trunk(nn.Module):
+    """torchvision mobilenet_v2 ``features[0:18]`` as a 4-level backbone (one of the backbones the reference's tests
+    name, tests/test_models.py:37).  vision_toolbox's own wrapper is absent from the snapshot; like the ResNet trunks
+     it returns the stride 4 / 8 / 16 / 32 maps: outputs of features[3], [6], [13], [17]
+    (24 / 32 / 96 / 320 channels); the final 1x1 conv to 1280 channels is the classifier's and is dropped.
+    Parameter names equal torchvision's (``features.<i>...``)."""
+
+    stride = 32
+    out_indices = (3, 6, 13, 17)
+
+    def __init__(self):
+        super().__init__()
+        import torchvision
+        self.features = torchvision.models.mobilenet_v2(weights=None).features[:18]
+        self.out_channels = [24, 32, 96, 320]
+
+    def get_out_channels(self) -> List[int]:
+        return list(self.out_channels)
+
+    def forward_features(self, x: torch.Tensor) -> List[torch.Tensor]:
+        outs = []
+        for i, f in enumerate(self.features):
+            x = f(x)
+            if i in self.out_indices:
+                outs.append(x)
+        return outs
+
+
+def make_conv(in_channels: int, out_channels: int, conv_type: str = "normal") -> nn.Sequential:
+    """models/layers.py:40-79 restated (kernel 3, the default): "normal" = conv3x3(no bias)-BN-ReLU; "separable" =
+    depthwise conv3x3(no bias)-BN-ReLU6 then pointwise conv1x1(no bias)-BN-ReLU6 (depth_multiplier 1).  Same Sequential
+    indices as the reference so that state dicts interchange."""
+    assert conv_type in ("separable", "normal")
+    if conv_type == "separable":
+        return nn.Sequential(
+            nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False), nn.BatchNorm2d(in_channels),
+            nn.ReLU6(inplace=True),
+            nn.Conv2d(in_channels, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels), nn.ReLU6(inplace=True))
+    return nn.Sequential(nn.Conv2d(in_channels, out_channels, 3, padding=1, bias=False), nn.BatchNorm2d(out_channels),
+                         nn.ReLU(inplace=True))
+
+
+class Fuse(nn.Module):
+    """models/layers.py:138-177 restated: the fusion node of BiFPNNeck / IDANeck.  Every input is projected to ``out``
+    channels by a 1x1 conv WITH bias when its channel count differs (:149-151); the LAST input is resized - nearest x2
+    (make_upsample's default, :81-99) or MaxPool2d(2, 2) (make_downsample's default, :119-136; Fuse passes its
+    ``downsample`` argument under a keyword make_downsample does not have, so the default always applies) - then
+    ``out = output_conv(sum_i w_i x_i / (sum_i w_i + eps))`` with w = relu(weights) (weighted_fusion) or the plain sum."""
+
+    def __init__(self, in_channels: List[int], out: int, resize: str, conv_type: str = "normal", weighted_fusion: bool = False):
+        super().__init__()
+        assert resize in ("up", "down")
+        self.project = nn.ModuleList([nn.Conv2d(c, out, 1) if c != out else None for c in in_channels])
+        self.weights = nn.Parameter(torch.ones(len(in_channels))) if weighted_fusion else None
+        self.resize = nn.Upsample(scale_factor=2, mode="nearest") if resize == "up" else nn.MaxPool2d(2, 2)
+        self.output_conv = make_conv(out, out, conv_type=conv_type)
+
+    def forward(self, *features, eps: float = 1e-6):
+        out = [p(x) if p is not None else x for p, x in zip(self.project, features)]
+        out[-1] = self.resize(out[-1])
+        if self.weights is not None:
+            w = F.relu(self.weights)
+            out = torch.stack([out[i] * w[i] for i in range(len(out))], dim=-1)
+            out = torch.sum(out, dim=-1) / (torch.sum(w) + eps)
+        else:
+            out = torch.sum(torch.stack(out, dim=-1), dim=-1)
+        return self.output_conv(out)
+
+
+class IDANeck(nn.Module):
+    """Iterative deep aggregation over the backbone's feature maps ("iteratively fuse consecutive feature maps from
+    backbone until there is only 1 feature map left", reference docs/implementation.md:43; the class itself is not in the
+    snapshot - models/__init__.py:2 - so the wiring is reconstructed from that sentence, from the Fuse node
+    (models/layers.py:138-177) and from DLA's IDA): level l+1 = [Fuse([c_i, c_{i+1}], c_i, "up")(f_i, f_{i+1}) for every
+    consecutive pair]; after len(in_channels)-1 levels one stride-4 map with in_channels[0] channels is left."""
+
+    def __init__(self, in_channels: List[int], conv_type: str = "normal", weighted_fusion: bool = False):
+        super().__init__()
+        self.stride = 2 ** (len(in_channels) - 1)
+        self.out_channels = in_channels[0]
+        self.levels = nn.ModuleList()
+        chans = list(in_channels)
+        while len(chans) > 1:
+            self.levels.append(nn.ModuleList([Fuse([chans[i], chans[i + 1]], chans[i], "up", conv_type=conv_type, weighted_fusion=weighted_fusion)
+                                              for i in range(len(chans) - 1)]))
+            chans = chans[:-1]
+
+    def get_out_channels(self) -> int:
+        return self.out_channels
+
+    def forward(self, feats: List[torch.Tensor]) -> torch.Tensor:
+        feats = list(feats)
+        for nodes in self.levels:
+            feats = [node(feats[i], feats[i + 1]) for i, node in enumerate(nodes)]
+        return feats[0]
+
+
+class BiFPNNeck(nn.Module):
+    """BiFPN (EfficientDet, reference docs/implementation.md:42) from the reference's Fuse nodes; class absent from the
+    snapshot, reconstructed: every level is first projected to ``out_channels`` by a 1x1 conv (with bias); each of the
+    ``num_layers`` layers runs a top-down pass td_i = Fuse([D, D], D, "up")(p_i, td_{i+1}) and a bottom-up pass
+    out_i = Fuse([D, D, D], D, "down")(p_i, td_i, out_{i-1}) (out_0 = td_0; the top level has no td input:
+    Fuse([D, D], D, "down")(p_top, out_{top-1})); the finest level of the last layer is returned (stride 4)."""
+
+    def __init__(self, in_channels: List[int], out_channels: int = 64, num_layers: int = 2, conv_type: str = "normal",
+                 weighted_fusion: bool = True):
+        super().__init__()
+        n = len(in_channels)
+        self.stride = 2 ** (n - 1)
+        self.out_channels = out_channels
+        d = out_channels
+        self.project = nn.ModuleList([nn.Conv2d(c, d, 1) for c in in_channels])
+        self.top_down = nn.ModuleList([nn.ModuleList([Fuse([d, d], d, "up", conv_type=conv_type, weighted_fusion=weighted_fusion) for _ in range(n - 1)])
+                                       for _ in range(num_layers)])
+        self.bottom_up = nn.ModuleList([nn.ModuleList([Fuse([d, d, d] if i < n - 2 else [d, d], d, "down", conv_type=conv_type, weighted_fusion=weighted_fusion)
+                                                       for i in range(n - 1)]) for _ in range(num_layers)])
+
+    def get_out_channels(self) -> int:
+        return self.out_channels
+
+    def forward(self, feats: List[torch.Tensor]) -> torch.Tensor:
+        p = [proj(f) for proj, f in zip(self.project, feats)]
+        n = len(p)
+        for td_nodes, bu_nodes in zip(self.top_down, self.bottom_up):
+            td = [None] * n
+            td[n - 1] = p[n - 1]
+            for i in range(n - 2, -1, -1):
+                td[i] = td_nodes[i](p[i], td[i + 1])
+            out = [td[0]] + [None] * (n - 1)
+            for i in range(1, n):
+                node = bu_nodes[i - 1]
+                out[i] = node(p[i], td[i], out[i - 1]) if i < n - 1 else node(p[i], out[i - 1])
+            p = out
+        return p[0]
+
+
 class FPN(nn.Module):
     """Top-down FPN that returns only the finest level.
 
@@ -240,12 +376,16 @@ def build_spec_model(num_classes: int = 80, backbone: str = "resnet34", neck: st
     reid_dim > 0 adds the tracking head (GenericHead(256, 64, **head_config))."""
     neck_config = dict(neck_config or {})
     head_config = dict(head_config or {})
-    bb = ResNetTrunk(backbone)
+    bb = MobileNetV2Trunk() if backbone == "mobilenet_v2" else ResNetTrunk(backbone)
     if neck == "FPN":
         neck_config.setdefault("out_channels", 256)
         nk = FPN(bb.get_out_channels(), **neck_config)
     elif neck in ("simple", "SimpleNeck"):
         nk = SimpleNeck(bb.get_out_channels(), **neck_config)
+    elif neck in ("ida", "IDANeck"):
+        nk = IDANeck(bb.get_out_channels(), **neck_config)
+    elif neck in ("bifpn", "BiFPNNeck"):
+        nk = BiFPNNeck(bb.get_out_channels(), **neck_config)
     else:
         raise ValueError(f"unknown neck {neck!r}")
     heads = nn.Module()
@@ -275,7 +415,7 @@ def synth_init(model: SpecModel, seed: int = 0, calib_size: int = 128, calib_bat
     g = torch.Generator().manual_seed(seed)
     for mod in model.modules():
         if isinstance(mod, nn.Conv2d):
-            fan_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1]
+            fan_in = mod.in_channels // mod.groups * mod.kernel_size[0] * mod.kernel_size[1]
             mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
             if mod.bias is not None and mod is not model.heads.heatmap.out_conv:
                 mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)    # heatmap keeps its prior bias
@@ -291,6 +431,10 @@ def synth_init(model: SpecModel, seed: int = 0, calib_size: int = 128, calib_bat
             blk.bn2.weight.mul_(0.5)
         elif isinstance(blk, Bottleneck):
             blk.bn3.weight.mul_(0.5)
+        elif type(blk).__name__ == "InvertedResidual" and blk.use_res_connect:
+            blk.conv[-1].weight.mul_(0.5)
+        elif type(blk).__name__ == "Fuse" and blk.weights is not None:      # fusion weights: positive, not all equal
+            blk.weights.copy_(torch.rand(blk.weights.shape, generator=g) + 0.5)
     for head in model.heads.children():
         head.out_conv.weight.mul_(out_gain / math.sqrt(2.0))
     # calibrate BN running stats with one train-mode pass (momentum=1 -> stats of this batch)

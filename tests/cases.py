@@ -72,6 +72,20 @@ FORWARD_CASES = {
                        seed=3, n=1, size=64, img_seed=10),
     "deconv4_64": dict(model=dict(num_classes=80, neck="simple", neck_config=dict(upsample_type="conv_transpose", deconv_kernel=4)),
                        seed=4, n=1, size=64, img_seed=11),
+    # SURVEY 8f rank 4 remainder (reference tests/test_models.py:37-39): mobilenet_v2 trunk (depthwise + pointwise stages, ReLU6),
+    # IDA / BiFPN necks from the reference's Fuse node (models/layers.py:138-177), make_conv's separable branch (:56-68)
+    "mbv2_fpn64": dict(model=dict(num_classes=8, backbone="mobilenet_v2", neck_config=dict(out_channels=64), head_config=dict(width=64, depth=1)),
+                       seed=5, n=2, size=64, img_seed=12, init=dict(out_gain=1.0)),
+    "mbv2_simple64": dict(model=dict(num_classes=8, backbone="mobilenet_v2", neck="simple", head_config=dict(width=64, depth=1)),
+                          seed=6, n=1, size=64, img_seed=13, init=dict(out_gain=1.0)),
+    "r18_ida64": dict(model=dict(num_classes=8, backbone="resnet18", neck="ida", head_config=dict(width=64, depth=1)),
+                      seed=7, n=2, size=64, img_seed=14, init=dict(out_gain=1.0)),
+    "r18_bifpn128": dict(model=dict(num_classes=8, backbone="resnet18", neck="bifpn", neck_config=dict(out_channels=64, num_layers=2),
+                                    head_config=dict(width=64, depth=1)), seed=8, n=1, size=128, img_seed=15, init=dict(out_gain=1.0)),
+    "mbv2_ida64_sep": dict(model=dict(num_classes=8, backbone="mobilenet_v2", neck="ida", neck_config=dict(conv_type="separable", weighted_fusion=True),
+                                      head_config=dict(width=64, depth=1)), seed=9, n=2, size=64, img_seed=16, init=dict(out_gain=1.0)),
+    "mbv2_bifpn64_sep": dict(model=dict(num_classes=8, backbone="mobilenet_v2", neck="bifpn", neck_config=dict(conv_type="separable", num_layers=1),
+                                        head_config=dict(width=64, depth=1)), seed=10, n=1, size=64, img_seed=17, init=dict(out_gain=1.0)),
 }
 
 

@@ -34,6 +34,8 @@ def main():
     assert ref_import.reference_available(), "run this where /root/reference exists"
     torch.set_num_threads(4)
     for case in cases.DECODE_CASES:
+        if len(sys.argv) > 1:
+            break
         heat, box, reid = cases.make_decode_inputs(case)
         probs = heat.sigmoid() if case["logits"] else heat
         out = ref_import.reference_decode(probs, box, num_detections=case["k"], nms_kernel=case["nms"],
@@ -43,8 +45,19 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"decode_{case['name']}.npz"), **arrs)
         print("decode", case["name"], {k: v.shape for k, v in arrs.items()})
 
+    only = set(sys.argv[1:])            # python gen_golden.py forward_<name> ...: (re)generate just those files
+    # IDA / BiFPN necks: the fusion nodes and separable convs of the golden model are the reference's OWN Fuse / make_conv
+    # classes (models/layers.py:40-79, 138-177) - the oracle's restatements are swapped out while the golden is made
+    ref_layers = ref_import.import_reference_layers()
     for name, kw in cases.FORWARD_CASES.items():
-        m = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"])
+        if only and f"forward_{name}" not in only:
+            continue
+        restated = spec_model.Fuse, spec_model.make_conv
+        spec_model.Fuse, spec_model.make_conv = ref_layers.Fuse, ref_layers.make_conv
+        try:
+            m = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"], **kw.get("init", {}))
+        finally:
+            spec_model.Fuse, spec_model.make_conv = restated
         rm = ref_import.reference_generic_model(m)
         x = cases.make_image(kw)
         with torch.no_grad():
@@ -57,6 +70,8 @@ def main():
     ref_trk = tracker_np.import_reference_tracker()
     import warnings
     for name, case in cases.TRACK_CASES.items():
+        if len(sys.argv) > 1:
+            break
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             t = ref_trk.Tracker(model=None, **case["tracker"])

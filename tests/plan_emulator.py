@@ -29,8 +29,25 @@ def run_plan(plan, image: torch.Tensor, act_dtype: Optional[torch.dtype] = None,
     bufs: Dict[str, torch.Tensor] = {"image": image}
     bufs.update(extra or {})
     for op in plan.ops:
+        if op.kind == "fuse":                       # dst = sum_i scale_i * src_i, the last source resized first
+            terms = []
+            for j, (name, sc) in enumerate(zip(op.srcs, op.scales)):
+                t = bufs[name]
+                if j == len(op.srcs) - 1 and op.resize == 1:
+                    t = F.interpolate(t, scale_factor=2.0, mode="nearest")
+                elif j == len(op.srcs) - 1 and op.resize == 2:
+                    t = F.max_pool2d(t, 2, 2)
+                terms.append(t * sc)
+            bufs[op.dst] = _q(sum(terms), act_dtype, split)
+            continue
         x = bufs[op.src]
-        if op.kind != "stem":
+        if op.kind == "dw":                         # depthwise 3x3, pad 1
+            w = _q(op.weight, act_dtype, split)
+            y = F.conv2d(x, w, op.bias, op.stride, 1, groups=x.shape[1])
+            y = F.relu6(y) if op.relu == 2 else (F.relu(y) if op.relu else y)
+            bufs[op.dst] = _q(y, act_dtype, split)
+            continue
+        if op.kind not in ("stem", "stem3x3"):
             x = x[:, op.src_c_off:op.src_c_off + op.cin]
         w = _q(op.weight, act_dtype, split)
         if op.kh:                                   # explicit window with top/left padding (transposed-conv phases)
@@ -44,7 +61,9 @@ def run_plan(plan, image: torch.Tensor, act_dtype: Optional[torch.dtype] = None,
             if op.residual_up == 2:
                 r = F.interpolate(r, scale_factor=2.0, mode="nearest")
             y = y + r
-        if op.relu:
+        if op.relu == 2:
+            y = F.relu6(y)
+        elif op.relu:
             y = F.relu(y)
         if op.kind == "stem":
             y = F.max_pool2d(y, 3, 2, 1)

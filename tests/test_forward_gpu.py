@@ -24,8 +24,9 @@ def _gold(name):
 def _build(kw, precision="split"):
     from centernet_lightning_b200.model import CenterNet
     spec = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"], **kw.get("init", {}))
-    net = CenterNet(kw["model"]["num_classes"], reid_dim=kw["model"].get("reid_dim", 0), box_multiplier=16.0, precision=precision,
-                    neck=kw["model"].get("neck", "FPN"), neck_config=kw["model"].get("neck_config"))
+    net = CenterNet(kw["model"]["num_classes"], kw["model"].get("backbone", "resnet34"), reid_dim=kw["model"].get("reid_dim", 0),
+                    box_multiplier=16.0, precision=precision, neck=kw["model"].get("neck", "FPN"),
+                    neck_config=kw["model"].get("neck_config"), head_config=kw["model"].get("head_config"))
     missing = net.model.load_state_dict(spec.state_dict(), strict=True)      # G2 key names are shared with the oracle
     return spec, net
 
@@ -332,7 +333,9 @@ def test_api_surface(cuda):
     with pytest.raises(RuntimeError, match="CPU"):
         net.model(torch.rand(1, 3, 64, 64))
     with pytest.raises(ValueError):
-        CenterNet(80, "resnet34", neck="bifpn")
+        CenterNet(80, "resnet34", neck="panet")                                 # not a neck of the reference
+    with pytest.raises(ValueError):
+        CenterNet(80, "resnet34", neck="ida", neck_config=dict(conv_type="deformable"))     # DCN is not lowered
 
 
 def test_config5_1024_input_large_maps(cuda):

@@ -101,7 +101,7 @@ def test_spec_model_param_counts_match_published():
 @pytest.mark.parametrize("name", list(cases.FORWARD_CASES))
 def test_spec_model_matches_reference_generic_model_golden(name):
     kw = cases.FORWARD_CASES[name]
-    m = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"])
+    m = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"], **kw.get("init", {}))
     with torch.no_grad():
         out = m(cases.make_image(kw))
     gold = _gold(f"forward_{name}")
@@ -133,3 +133,26 @@ def test_preprocess_oracle_properties():
         np.testing.assert_allclose(col, textbook, rtol=3e-7, atol=3e-7)
     chw = preprocess_np.to_chw(out)
     assert chw.shape == (3, 16, 16) and chw.flags["C_CONTIGUOUS"]
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("conv_type,weighted,resize,chans", [("normal", False, "up", [64, 128]), ("separable", True, "up", [32, 32]),
+                                                             ("normal", True, "down", [64, 64, 64]), ("separable", False, "down", [24, 64])])
+def test_fuse_and_make_conv_restatements_match_live_reference(conv_type, weighted, resize, chans):
+    """oracle.spec_model.Fuse / make_conv against the reference's own classes (models/layers.py:40-79, 138-177) with the same
+    parameters: identical outputs."""
+    layers = ref_import.import_reference_layers()
+    torch.manual_seed(5)
+    ref = layers.Fuse(chans, 64, resize, conv_type=conv_type, weighted_fusion=weighted).eval()
+    mine = spec_model.Fuse(chans, 64, resize, conv_type=conv_type, weighted_fusion=weighted).eval()
+    with torch.no_grad():
+        for mod in ref.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5); mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.1)
+        if weighted:
+            ref.weights.copy_(torch.rand(len(chans)) + 0.2)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    s = 8
+    xs = [torch.randn(2, c, s, s) for c in chans[:-1]] + [torch.randn(2, chans[-1], s // 2 if resize == "up" else s * 2, s // 2 if resize == "up" else s * 2)]
+    with torch.no_grad():
+        assert torch.equal(ref(*xs), mine(*xs))

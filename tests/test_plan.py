@@ -136,3 +136,71 @@ def test_resnet50_bottleneck_plan_reproduces_oracle():
     out = run_plan(pl, x)
     for k in ref:
         np.testing.assert_allclose(out[k].numpy(), ref[k].numpy(), rtol=0, atol=2e-4)
+
+
+BREADTH = ["mbv2_fpn64", "mbv2_simple64", "r18_ida64", "r18_bifpn128", "mbv2_ida64_sep", "mbv2_bifpn64_sep"]
+
+
+@pytest.mark.parametrize("case", BREADTH)
+def test_breadth_plans_reproduce_oracle(case):
+    """SURVEY 8f rank 4 remainder: MobileNetV2 (depthwise + pointwise stages, ReLU6, channels zero-padded to multiples of
+    64), IDA / BiFPN necks lowered from the reference's Fuse node (models/layers.py:138-177) and make_conv's separable
+    branch (:56-68): the op list reproduces the oracle graph in fp32."""
+    kw = cases.FORWARD_CASES[case]
+    m = spec_model.synth_init(spec_model.build_spec_model(**kw["model"]), seed=kw["seed"], **kw.get("init", {}))
+    pl = P.build_plan(m.state_dict(), backbone=kw["model"].get("backbone", "resnet34"), neck=kw["model"].get("neck", "FPN"),
+                      head_depth=kw["model"]["head_config"]["depth"])
+    x = cases.make_image(kw)
+    with torch.no_grad():
+        ref = m(x)
+    out = run_plan(pl, x)
+    for k in ref:
+        assert out[k].shape == ref[k].shape
+        np.testing.assert_allclose(out[k].numpy(), ref[k].numpy(), rtol=0, atol=5e-4)
+    kinds = {op.kind for op in pl.ops}
+    if "mbv2" in case:
+        assert {"stem3x3", "dw", "conv"} <= kinds
+        assert all(b.channels % 64 == 0 for b in pl.buffers.values() if not b.fp32_nchw)
+    if "bifpn" in case or "sep" in case:
+        assert "fuse" in kinds
+    # the hi+lo fp16 operand storage of the engine keeps these graphs inside the parity bar as well
+    split = run_plan(pl, x, act_dtype=torch.float16, split=True)
+    for k in ref:
+        assert (split[k] - ref[k]).abs().max() < 1e-3
+
+
+def test_fuse_lowering_folds_the_fusion_weights():
+    """Weighted fusion (reference models/layers.py:167-171): out = sum_i relu(w_i) x_i / (sum_j relu(w_j) + 1e-6).  Projected
+    inputs carry their weight inside the 1x1 conv; un-projected ones in the fuse op's scale; a negative weight is clamped."""
+    torch.manual_seed(0)
+    node = spec_model.Fuse([64, 128, 64], 64, "down", conv_type="separable", weighted_fusion=True).eval()
+    with torch.no_grad():
+        node.weights.copy_(torch.tensor([0.7, -0.3, 1.9]))
+        for mod in node.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+    sd = {f"n.{k}": v for k, v in node.state_dict().items()}
+    pl = P.Plan()
+    for name, c, s in (("a", 64, 8), ("b", 128, 8), ("c", 64, 4)):
+        pl.add_buffer(name, c, s)
+    out = P._Lowering(pl, sd).fuse("n", "n", [("a", 64), ("b", 128), ("c", 64)], 64, 8, "down")
+    fuse = next(op for op in pl.ops if op.kind == "fuse")
+    w = torch.relu(node.weights.detach().double())
+    assert fuse.resize == 2 and len(fuse.srcs) == 3
+    assert abs(fuse.scales[0] - float(w[0] / (w.sum() + 1e-6))) < 1e-12 and fuse.scales[1] == 1.0       # b is projected: weight (0) folded
+    a, b, c = torch.rand(1, 64, 8, 8), torch.rand(1, 128, 8, 8), torch.rand(1, 64, 16, 16)
+    # run the op list by hand (the emulator starts from the image): same arithmetic as tests/plan_emulator.py
+    import torch.nn.functional as F
+    bufs = {"a": a, "b": b, "c": c}
+    for op in pl.ops:
+        if op.kind == "fuse":
+            terms = [bufs[s] * sc for s, sc in zip(op.srcs[:-1], op.scales[:-1])] + [F.max_pool2d(bufs[op.srcs[-1]], 2, 2) * op.scales[-1]]
+            bufs[op.dst] = sum(terms)
+        elif op.kind == "dw":
+            bufs[op.dst] = F.relu6(F.conv2d(bufs[op.src], op.weight, op.bias, 1, 1, groups=op.cin))
+        else:
+            y = F.conv2d(bufs[op.src], op.weight, op.bias, 1, op.pad)
+            bufs[op.dst] = F.relu6(y) if op.relu == 2 else y
+    with torch.no_grad():
+        ref = node(a, b, c)
+    np.testing.assert_allclose(bufs[out].numpy(), ref.numpy(), rtol=0, atol=2e-5)
