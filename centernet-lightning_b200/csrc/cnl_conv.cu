@@ -178,25 +178,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 
   if (warp == 0) {
     // ===================================== TMA producer ==============================================
-    if (ROWS && lane == 0) {
+    if (ROWS && ptx::elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      int n_loads = 0;                                     // input rows loaded so far (slot = n_loads % a_slots)
+      int ld_slot = 0;                                     // ring position of the next input-row load and the parity of its
+      uint32_t ld_par = 0;                                 // slot's barriers (counters instead of n_loads % / a_slots)
       const int row_bytes = p.box_w * kBlockK * 2;
       for (int t = rows_t0; t < rows_t1; ++t) {
         const int strip = t / p.tiles_h, h = t - strip * p.tiles_h;
         const int img = strip / p.tiles_w, w0 = (strip - img * p.tiles_w) * p.tw;
         const bool fresh = (t == rows_t0) || (h == 0);     // first output row of this CTA's run or of a new strip
         const int n_new = fresh ? p.kh : 1;
-        for (int q = 0; q < n_new; ++q, ++n_loads) {
+        for (int q = 0; q < n_new; ++q) {
           const int in_row = h - p.pad_h + (fresh ? q : p.kh - 1);
-          const int slot = n_loads % p.a_slots;
-          ptx::mbar_wait(&a_empty_bar[slot], ((n_loads / p.a_slots) & 1) ^ 1);
+          const int slot = ld_slot;
+          ptx::mbar_wait(&a_empty_bar[slot], ld_par ^ 1);
           ptx::mbar_arrive_expect_tx(&a_full_bar[slot], NPLANE * row_bytes);
 #pragma unroll
           for (int pl = 0; pl < NPLANE; ++pl)
             ptx::tma_load_4d(a_ring + ((size_t)slot * NPLANE + pl) * p.a_slot_bytes, &src_map, &a_full_bar[slot], p.src_c_off,
                              w0 - p.pad_w, in_row, img + pl * p.n_img);
+          if (++ld_slot == p.a_slots) { ld_slot = 0; ld_par ^= 1; }
         }
         for (int tap = 0; tap < taps; ++tap) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -209,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
       }
     }
-    if (PAIR && lane == 0) {
+    if (PAIR && ptx::elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.n_tile / 2;
@@ -243,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
       }
     }
-    if (!ROWS && !PAIR && lane == 0) {
+    if (!ROWS && !PAIR && ptx::elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.n_tile / csize;
@@ -285,57 +287,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =================================================
-    if (ROWS && lane == 0) {
-      // row-rolling issue loop: always the cat form (N = 2*n_tile for hi x [hi|lo], N = n_tile for lo x hi)
+    if (ROWS && ptx::elect_one_sync()) {
+      // row-rolling issue loop: always the cat form (N = 2*n_tile for hi x [hi|lo], N = n_tile for lo x hi).
+      // ONE thread issues 8 small MMAs (N = 128 / 64: 64 / 32 tensor-pipe cycles each) per tap, so the scalar work between
+      // them is what bounds this kernel: measured (ncu source view, r2) 181 SASS instructions per tap - two integer
+      // divisions (tap / kw, load index % slots) and an ELECT / BRA.U.ANY loop around every uniform-datapath instruction of
+      // the divergent `lane == 0` branch - kept the tensor pipe at 37 %.  Hence elect.sync, slot / parity counters instead
+      // of div / mod, and descriptors advanced by adds.
       const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
       const uint32_t idesc_cat = ptx::make_idesc_f16_m128((uint32_t)p.n_tile * 2u);
+      const uint64_t desc_hi_bits = ptx::make_sw128_kmajor_desc(0);          // everything but the 14 address bits
+      const uint32_t ring_addr = ptx::smem_u32(a_ring), stages_addr = ptx::smem_u32(stages);
+      const uint32_t slot_stride = (uint32_t)(NPLANE * p.a_slot_bytes);
       int stage = 0;
       uint32_t phase = 0;
-      int n_loads = 0, acc_it = 0;
+      int ld_slot = 0, first_slot = 0;                      // ring position of the next load / of input row h - pad_h
+      uint32_t ld_par = 0;
+      int h = rows_t0 % p.tiles_h;
+      uint32_t acc_it = 0;
       for (int t = rows_t0; t < rows_t1; ++t, ++acc_it) {
-        const int h = t % p.tiles_h;
         const bool fresh = (t == rows_t0) || (h == 0);
         const bool last = (t + 1 == rows_t1) || (h == p.tiles_h - 1);   // the rows in the ring die with this output row
         const int n_new = fresh ? p.kh : 1;
-        const int as = two_acc ? (acc_it & 1) : 0;
-        const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
+        const uint32_t as = two_acc ? (acc_it & 1u) : 0u;
+        const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1u) : (acc_it & 1u);
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        for (int q = 0; q < n_new; ++q, ++n_loads) ptx::mbar_wait(&a_full_bar[n_loads % p.a_slots], (n_loads / p.a_slots) & 1);
+        if (fresh) first_slot = ld_slot;
+        else if (++first_slot == p.a_slots) first_slot = 0;
+        for (int q = 0; q < n_new; ++q) {
+          ptx::mbar_wait(&a_full_bar[ld_slot], ld_par);
+          if (++ld_slot == p.a_slots) { ld_slot = 0; ld_par ^= 1; }
+        }
         ptx::tc_fence_after();
-        const int first_load = n_loads - p.kh;               // load index of input row h - pad_h
         const uint32_t d_tmem = tmem_base + as * 256;
         const uint32_t d_corr = d_tmem + p.corr_off;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.kw, sx = tap - r * p.kw;
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const int slot = (first_load + r) % p.a_slots;
-          const uint32_t a_addr = ptx::smem_u32(a_ring + (size_t)slot * NPLANE * p.a_slot_bytes) + sx * (kBlockK * 2);
-          const uint32_t b_addr = ptx::smem_u32(stages + (size_t)stage * stage_bytes);
-          // (descriptor base-offset field stays 0: measured on B200, the swizzle phase comes from the address bits)
-          const uint64_t a_hi = ptx::make_sw128_kmajor_desc(a_addr);
-          const uint64_t a_lo = ptx::make_sw128_kmajor_desc(a_addr + p.a_slot_bytes);
-          const uint64_t b_hi = ptx::make_sw128_kmajor_desc(b_addr);
+        uint32_t first_mma = 0;                               // 0 only for the first MMA of the tile (overwrite the accumulator)
+        int slot = first_slot;
+        for (int r = 0; r < p.kh; ++r) {
+          const uint32_t a_row = ring_addr + (uint32_t)slot * slot_stride;
+          for (int sx = 0; sx < p.kw; ++sx) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            // (descriptor base-offset field stays 0: measured on B200, the swizzle phase comes from the address bits)
+            const uint32_t a_addr = a_row + (uint32_t)sx * (kBlockK * 2);
+            const uint32_t b_addr = stages_addr + (uint32_t)stage * (uint32_t)stage_bytes;
+            const uint64_t a_hi = desc_hi_bits | (uint64_t)((a_addr & 0x3ffffu) >> 4);
+            const uint64_t a_lo = desc_hi_bits | (uint64_t)(((a_addr + (uint32_t)p.a_slot_bytes) & 0x3ffffu) >> 4);
+            const uint64_t b_hi = desc_hi_bits | (uint64_t)((b_addr & 0x3ffffu) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t koff = (uint64_t)((k * 32) >> 4);
-            ptx::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, (tap | k) != 0);
-            if (NPLANE == 2) ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t koff = (uint64_t)((k * 32) >> 4);
+              ptx::umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc_cat, first_mma);
+              first_mma = 1;
+              if (NPLANE == 2) ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
           // The oldest input row (h - pad_h) is read by the r = 0 taps only: hand its slot back as soon as they are issued, so
           // that the producer can refill it with the row the NEXT output row needs while the remaining taps still run.  A
-          // ring of kh slots then suffices and the shared memory goes to weight stages instead - the weight-tile latency
-          // (~1.2 us per 16 KB tile against ~0.2 us of MMA work per tap) is what bounds this kernel, not bandwidth.
-          if (tap == p.kw - 1) ptx::umma_commit(&a_empty_bar[first_load % p.a_slots]);
+          // ring of kh slots then suffices and the shared memory goes to weight stages instead.  At the end of a strip / run
+          // the other rows die as well.
+          if (r == 0 || last) ptx::umma_commit(&a_empty_bar[slot]);
+          if (++slot == p.a_slots) slot = 0;
         }
-        // at the end of a strip / run the other rows die as well
-        if (last) for (int r = 1; r < p.kh; ++r) ptx::umma_commit(&a_empty_bar[(first_load + r) % p.a_slots]);
         ptx::umma_commit(&tmem_full_bar[as]);
+        if (++h == p.tiles_h) h = 0;
       }
     }
-    if (PAIR && lane == 0 && crank == 0) {
+    if (PAIR && crank == 0 && ptx::elect_one_sync()) {
       // leader of the CTA pair: M = 256 (128 accumulator rows in each CTA's tensor memory), N = n_tile
       const uint32_t idesc = ptx::make_idesc_f16_m256((uint32_t)p.n_tile);
       int stage = 0;
@@ -372,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         ptx::umma_commit_pair(&tmem_full_bar[as], 0b11);        // both CTAs' epilogues may read their accumulator rows
       }
     }
-    if (!ROWS && !PAIR && lane == 0) {
+    if (!ROWS && !PAIR && ptx::elect_one_sync()) {
       const uint32_t idesc = ptx::make_idesc_f16_m128((uint32_t)p.n_tile);
       // cat: the hi and lo weight tiles sit back to back in the stage (n_tile rows of 128 B each, whole swizzle atoms),
       // so A_hi x [B_hi | B_lo] is ONE instruction of N = 2*n_tile whose columns [n_tile, 2*n_tile) are the correction
@@ -481,6 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         ptx::mbar_wait(&tmem_full_bar[as], aphase);
         ptx::tc_fence_after();
 
+        const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;     // first pixel of this warp's 32 (store box origin)
         auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4]) {
           uint32_t r[32];
           float v[32];
@@ -562,7 +583,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;
             if (p.dst_up == 2) {
               // destination at twice the resolution, viewed as [n][y][py][x][px*C + c]: one store per sub-pixel.
               // All four = conv followed by a nearest x2 upsample; a single one = one phase of a stride-2 transposed conv.

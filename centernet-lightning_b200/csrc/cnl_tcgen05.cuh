@@ -122,6 +122,21 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+// One lane of a converged warp (elect.sync): the single-thread roles (TMA producer, MMA issuer) are entered through this
+// instead of `lane == 0`.  ptxas then knows that exactly one thread runs the region and issues the uniform-datapath
+// instructions (UTCHMMA, UTCBAR, UTMALDG) directly; under a plain divergent `if` it wraps every one of them in an
+// ELECT / BRA.U.ANY serialisation loop (5 extra instructions per tcgen05.mma in the issue loop).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 __device__ __forceinline__ void grid_dependents_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
