@@ -43,6 +43,7 @@ constexpr int kConvThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..
 constexpr int kEpiWarps = 8;
 constexpr int kSmemLimit = 232448 - 1024;    // 227 KB opt-in shared memory per CTA minus the static part (barriers)
 constexpr int kStageWarpBytes = 32 * 64;     // epilogue staging: 32 pixels x 32 channels fp16 per warp and plane
+constexpr int kParamBias = 1024;             // bias values carried in the kernel parameters (constant bank)
 
 struct ConvParams {
   int n_img, out_h, out_w;
@@ -75,6 +76,13 @@ struct ConvParams {
   int a_slot_bytes;             // bytes of one slot and plane: (tw + kw - 1) pixels x 128 B, rounded up to 1024
   int box_w;                    // pixels per loaded row: tw + kw - 1
   int stage_depth;              // epilogue staging buffers per warp (ring): TMA stores of the last depth-1 chunks may still be in flight
+  int w_resident;               // ROWS: every tap's weight tile stays in its own stage for the whole launch (num_stages == taps)
+  // The per-channel bias travels in the kernel parameters: the epilogue reads it through the constant cache (one broadcast
+  // LDC per value).  As __ldg loads from global memory the same values missed L1 on every tile - 226 KB of the SM's 256 KB
+  // are shared memory, and the epilogue's own stores / residual loads evict the three bias lines - and 30-35 % of all warp
+  // stall samples of the bandwidth-bound ops (head out-convs, FPN laterals) sat on those loads (ncu source view, r2).
+  int bias_in_params;           // 0: more than kParamBias channels, read p.bias from global memory instead
+  float bias_c[kParamBias];
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -184,9 +192,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
       int ld_slot = 0;                                     // ring position of the next input-row load and the parity of its
       uint32_t ld_par = 0;                                 // slot's barriers (counters instead of n_loads % / a_slots)
       const int row_bytes = p.box_w * kBlockK * 2;
+      if (p.w_resident && rows_t0 < rows_t1) {
+        // the whole weight tensor (taps x [hi|lo] tiles) fits beside the row ring: load it ONCE; the issue loop then never
+        // waits for a weight tile again (per output row the stem re-fetched 64 KB of weights for 32 KB of input)
+        for (int tap = 0; tap < taps; ++tap) {
+          ptx::mbar_arrive_expect_tx(&full_bar[tap], stage_bytes);
+          uint8_t* st = stages + (size_t)tap * stage_bytes;
+#pragma unroll
+          for (int pl = 0; pl < NPLANE; ++pl)
+            ptx::tma_load_3d(st + pl * b_tile_bytes, &w_map, &full_bar[tap], 0, 0, tap + pl * taps);
+        }
+      }
+      // (image, column strip, row) of the next tile, advanced by adds
+      int strip = rows_t0 / p.tiles_h, h = rows_t0 - strip * p.tiles_h;
+      int img = strip / p.tiles_w, w0 = (strip - img * p.tiles_w) * p.tw;
       for (int t = rows_t0; t < rows_t1; ++t) {
-        const int strip = t / p.tiles_h, h = t - strip * p.tiles_h;
-        const int img = strip / p.tiles_w, w0 = (strip - img * p.tiles_w) * p.tw;
         const bool fresh = (t == rows_t0) || (h == 0);     // first output row of this CTA's run or of a new strip
         const int n_new = fresh ? p.kh : 1;
         for (int q = 0; q < n_new; ++q) {
@@ -200,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                              w0 - p.pad_w, in_row, img + pl * p.n_img);
           if (++ld_slot == p.a_slots) { ld_slot = 0; ld_par ^= 1; }
         }
-        for (int tap = 0; tap < taps; ++tap) {
+        for (int tap = 0; tap < taps && !p.w_resident; ++tap) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           uint8_t* st = stages + (size_t)stage * stage_bytes;
@@ -209,6 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             ptx::tma_load_3d(st + pl * b_tile_bytes, &w_map, &full_bar[stage], 0, 0, tap + pl * taps);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
+        if (++h == p.tiles_h) { h = 0; w0 += p.tw; if (w0 >= p.tiles_w * p.tw) { w0 = 0; ++img; } }
       }
     }
     if (PAIR && ptx::elect_one_sync()) {
@@ -326,7 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         for (int r = 0; r < p.kh; ++r) {
           const uint32_t a_row = ring_addr + (uint32_t)slot * slot_stride;
           for (int sx = 0; sx < p.kw; ++sx) {
-            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::mbar_wait(&full_bar[stage], phase);           // (resident weights: phase stays 0, the wait falls through)
             ptx::tc_fence_after();
             // (descriptor base-offset field stays 0: measured on B200, the swizzle phase comes from the address bits)
             const uint32_t a_addr = a_row + (uint32_t)sx * (kBlockK * 2);
@@ -341,8 +362,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
               first_mma = 1;
               if (NPLANE == 2) ptx::umma_f16(d_corr, a_lo + koff, b_hi + koff, idesc, 1);
             }
-            ptx::umma_commit(&empty_bar[stage]);
-            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+            if (!p.w_resident) ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == p.num_stages) { stage = 0; if (!p.w_resident) phase ^= 1; }
           }
           // The oldest input row (h - pad_h) is read by the r = 0 taps only: hand its slot back as soon as they are issued, so
           // that the producer can refill it with the row the NEXT output row needs while the remaining taps still run.  A
@@ -450,17 +471,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     int sbuf = 0;                                       // ring position inside this warp's staging buffers
     int acc_it = 0;
     const int it_begin = ROWS ? rows_t0 : group0, it_end = ROWS ? rows_t1 : total_groups, it_step = ROWS ? 1 : group_step;
+    // this thread's pixel and this warp's first pixel inside a tile: the same for every tile (the short-K tiles of the stem /
+    // layer1 run one tile per ~1500-3500 tensor-pipe cycles, where five integer divisions per tile in every epilogue thread showed)
+    const int pix = lane_base + lane;
+    const int pix_dh = pix / p.tw, pix_dw = pix - pix_dh * p.tw;
+    const int lb_dh = lane_base / p.tw, lb_dw = lane_base - lb_dh * p.tw;
+    int r_strip = ROWS ? it_begin / p.tiles_h : 0;
+    int r_h = ROWS ? it_begin - r_strip * p.tiles_h : 0;
+    int r_img = ROWS ? r_strip / p.tiles_w : 0;
+    int r_w0 = ROWS ? (r_strip - r_img * p.tiles_w) * p.tw : 0;
     for (int grp = it_begin; grp < it_end; grp += it_step, ++acc_it) {
       const int as = two_acc ? (acc_it & 1) : 0;
       const uint32_t aphase = two_acc ? ((acc_it >> 1) & 1) : (acc_it & 1);
       int n_idx, img, h0, w0;
       bool dummy = false;
       if (ROWS) {
-        const int strip = grp / p.tiles_h;
         n_idx = 0;
-        h0 = grp - strip * p.tiles_h;                      // th == 1
-        img = strip / p.tiles_w;
-        w0 = (strip - img * p.tiles_w) * p.tw;
+        h0 = r_h; img = r_img; w0 = r_w0;                  // th == 1; advanced by adds at the end of the iteration
+        if (++r_h == p.tiles_h) { r_h = 0; r_w0 += p.tw; if (r_w0 >= p.tiles_w * p.tw) { r_w0 = 0; ++r_img; } }
       } else {
         n_idx = grp % p.n_tiles;
         int m_idx = (grp / p.n_tiles) * csize + crank;
@@ -471,8 +499,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         h0 = (m_idx / p.tiles_w) * p.th;
         w0 = (m_idx % p.tiles_w) * p.tw;
       }
-      const int pix = lane_base + lane;
-      const int h = h0 + pix / p.tw, w = w0 + pix % p.tw;
+      const int h = h0 + pix_dh, w = w0 + pix_dw;
       const bool valid = !dummy && (h < p.out_h) && (w < p.out_w);
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + as * 256;
 
@@ -501,7 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         ptx::mbar_wait(&tmem_full_bar[as], aphase);
         ptx::tc_fence_after();
 
-        const int hq = h0 + lane_base / p.tw, wq = w0 + lane_base % p.tw;     // first pixel of this warp's 32 (store box origin)
+        const int hq = h0 + lb_dh, wq = w0 + lb_dw;           // first pixel of this warp's 32 (store box origin)
         auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4]) {
           uint32_t r[32];
           float v[32];
@@ -519,12 +546,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           }
           const int cb = n_idx * p.n_tile + c32 * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
-            v[j + 0] = fmaf(v[j + 0], p.wscale_inv, b4.x);
-            v[j + 1] = fmaf(v[j + 1], p.wscale_inv, b4.y);
-            v[j + 2] = fmaf(v[j + 2], p.wscale_inv, b4.z);
-            v[j + 3] = fmaf(v[j + 3], p.wscale_inv, b4.w);
+          if (p.bias_in_params) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.wscale_inv, p.bias_c[cb + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+              v[j + 0] = fmaf(v[j + 0], p.wscale_inv, b4.x);
+              v[j + 1] = fmaf(v[j + 1], p.wscale_inv, b4.y);
+              v[j + 2] = fmaf(v[j + 2], p.wscale_inv, b4.z);
+              v[j + 3] = fmaf(v[j + 3], p.wscale_inv, b4.w);
+            }
           }
           if (res_px != nullptr) {
 #pragma unroll
@@ -636,7 +669,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           for (int j = 0; j < 16; ++j) {
             const int c = cb + j;
             if (valid && c < p.cout_real) {
-              float val = fmaf(v[j], p.wscale_inv, __ldg(p.bias + c));
+              float val = fmaf(v[j], p.wscale_inv, p.bias_in_params ? p.bias_c[c] : __ldg(p.bias + c));
               if (p.relu) val = fmaxf(val, 0.0f);
               if (p.relu == 2) val = fminf(val, 6.0f);
               if (p.sigmoid) val = sigmoid32(val);         // the kernel is HBM-bound: the logistic hides behind the loads
@@ -1010,6 +1043,7 @@ struct OpInfo {
   int cout_pad, n_tile, n_tiles, tw, th, tiles_w, tiles_h, num_stages, store_w, store_h, cluster, acc_stages, corr_off, cat;
   int kh, kw, pad_h, pad_w, up;         // resolved kernel extent / padding, destination scale (1 or 2)
   int rows, a_slots, a_slot_bytes, box_w; // ROWS mode geometry (rows = 0: im2col tiles)
+  int w_resident;                         // ROWS: weights loaded once per CTA (one stage per tap)
   int pair;                               // CTA-pair (cta_group::2) form
   int stage_depth;                        // epilogue staging ring depth (1..3)
   bool corr;                          // SPLIT precision: separate correction accumulator (long reductions) or fused
@@ -1230,7 +1264,7 @@ static void pack_split_weights(OpInfo& op, const std::vector<float>& w /*[cout][
 }
 
 static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhwc_out, int precision) {
-  op.rows = 0; op.a_slots = 0; op.a_slot_bytes = 0; op.box_w = 0;
+  op.rows = 0; op.a_slots = 0; op.a_slot_bytes = 0; op.box_w = 0; op.w_resident = 0;
   if (!rows_enabled() || precision != CNL_PRECISION_SPLIT || !op.cat || planes != 2) return false;
   if (cin != 64 || stride != 1 || op.th != 1 || op.n_tiles != 1 || op.kh * op.kw < 2 || op.cluster != 1 || !nhwc_out) return false;
   const int box_w = op.tw + op.kw - 1;
@@ -1250,6 +1284,21 @@ static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhw
     b_stages = (kSmemLimit - 1024 - staging - slots * planes * slot_bytes) / b_stage;
     if (b_stages >= kMinRowsStages || extra_env >= 0) break;
   }
+  // Resident weights: when every tap's [hi|lo] tile fits beside a ring of kh slots (the stem: 4 taps x 16 KB), each tap
+  // keeps its own stage for the whole launch and is loaded once per CTA (CNL_ROWS_RESIDENT=0 for A/B timing).
+  static const bool resident_on = [] { const char* v = getenv("CNL_ROWS_RESIDENT"); return !(v && atoi(v) == 0); }();
+  const int taps = op.kh * op.kw;
+  op.w_resident = 0;
+  if (resident_on && taps <= kMaxStages) {
+    for (int extra = 1; extra >= 0; --extra) {
+      const int rs = op.kh + extra;
+      if (rs <= kMaxStages && kSmemLimit - 1024 - staging - rs * planes * slot_bytes >= taps * b_stage) {
+        op.rows = 1; op.a_slots = rs; op.a_slot_bytes = slot_bytes; op.box_w = box_w;
+        op.num_stages = taps; op.w_resident = 1;
+        return true;
+      }
+    }
+  }
   // fewer than three weight stages in flight and the kernel waits on weight-tile latency instead
   if (b_stages < 3 || slots > kMaxStages) return false;
   op.rows = 1; op.a_slots = slots; op.a_slot_bytes = slot_bytes; op.box_w = box_w;
@@ -1264,7 +1313,7 @@ static int prepare_elementwise(cnl_engine* e, OpInfo& op) {
   const BufferInfo& dst = e->bufs[d.dst];
   op.rows = 0; op.pair = 0; op.corr = false; op.cat = 0; op.cluster = 1; op.num_stages = 0; op.stage_depth = 0; op.a_slots = 0; op.n_tile = 0;
   op.wscale = 1.0f; op.up = 1; op.kh = op.kw = 3; op.pad_h = op.pad_w = 1; op.acc_stages = 0; op.corr_off = 0; op.tw = op.th = 0; op.tiles_w = op.tiles_h = 0;
-  op.store_w = op.store_h = 0; op.n_tiles = 0; op.cout_pad = 0; op.a_slot_bytes = 0; op.box_w = 0;
+  op.store_w = op.store_h = 0; op.n_tiles = 0; op.cout_pad = 0; op.a_slot_bytes = 0; op.box_w = 0; op.w_resident = 0;
   if (dst.fp32_nchw || dst.channels % 8) return fail(CNL_ERR_UNSUPPORTED, "depthwise / fuse / stem3x3 ops write NHWC buffers with C %% 8 == 0");
   if (d.kind == 2) {
     const BufferInfo& src = e->bufs[d.src];
@@ -1578,11 +1627,14 @@ int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int f
     p.sigmoid = (sigmoid_buffer >= 0 && d.dst == sigmoid_buffer) ? 1 : 0;
     p.wscale_inv = 1.0f / op.wscale;
     p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
+    p.bias_in_params = (d.kind <= 1 && op.bias_packed.size() <= (size_t)kParamBias) ? 1 : 0;
+    if (p.bias_in_params) std::memcpy(p.bias_c, op.bias_packed.data(), op.bias_packed.size() * sizeof(float));
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
     p.acc_stages = op.acc_stages; p.corr_off = op.corr_off; p.cat = op.cat;
     p.dst_up = 1; p.dst_phase = -1; p.dst_c = dst.channels;
     p.a_slots = op.a_slots; p.a_slot_bytes = op.a_slot_bytes; p.box_w = op.box_w; p.stage_depth = op.stage_depth;
+    p.w_resident = op.rows ? op.w_resident : 0;
     if (d.kind == 1) {
       if (!image) return fail(CNL_ERR_INVALID_ARGUMENT, "cnl_engine_forward: image pointer required for the stem");
       const int SH = e->height / 2, SW = e->width / 2;
