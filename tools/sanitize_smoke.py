@@ -35,6 +35,13 @@ print({k: tuple(v.shape) for k, v in net2.detect(torch.rand((1, 3, 64, 96), devi
 net3 = CenterNet(4, backbone="resnet18", neck="simple", neck_config={"upsample_channels": (64, 64, 64)},
                  head_config={"width": 64, "depth": 1}, num_detections=10).init_synthetic_(1).to(dev)
 print({k: tuple(v.shape) for k, v in net3.detect(torch.rand((1, 3, 64, 96), device=dev), use_graph=False).items()})
+# MobileNetV2 trunk (3x3/2 stem, depthwise 3x3, ReLU6, Cout tiles of 192) + BiFPN / IDA necks (fuse kernel, separable convs)
+net4 = CenterNet(4, backbone="mobilenet_v2", neck="bifpn", neck_config={"conv_type": "separable", "num_layers": 1},
+                 head_config={"width": 64, "depth": 1}, num_detections=10).init_synthetic_(2).to(dev)
+print({k: tuple(v.shape) for k, v in net4.detect(torch.rand((1, 3, 64, 96), device=dev), use_graph=False).items()})
+net5 = CenterNet(4, backbone="resnet18", neck="ida", neck_config={"weighted_fusion": True},
+                 head_config={"width": 64, "depth": 1}, num_detections=10).init_synthetic_(3).to(dev)
+print({k: tuple(v.shape) for k, v in net5.detect(torch.rand((1, 3, 64, 64), device=dev), use_graph=False).items()})
 # loader + tracker kernels
 from centernet_lightning_b200 import preprocess  # noqa: E402
 from centernet_lightning_b200.tracker import CostMatrices  # noqa: E402
