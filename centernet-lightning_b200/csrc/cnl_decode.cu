@@ -464,7 +464,7 @@ __device__ __forceinline__ float4 decode_box_from(const float (&g)[4], int idx, 
     float gv = g[c];
     if (box_log) gv = expf(gv);
     gv = __fmul_rn(gv, mult);
-    s[c] = fmaxf(gv, 0.0f);
+    s[c] = (gv < 0.0f) ? 0.0f : gv;            // torch.clamp_min(x, 0): a NaN stays NaN (fmaxf would return 0)
   }
   float x1 = __fsub_rn(cx, s[0]), y1 = __fsub_rn(cy, s[1]);
   float x2 = __fadd_rn(cx, s[2]), y2 = __fadd_rn(cy, s[3]);
