@@ -793,6 +793,59 @@ stem_im2row_kernel(const float* __restrict__ image, __half* __restrict__ T, int 
   }
 }
 
+// Space-to-depth form of the image for the stem (default since round 2; CNL_STEM_IM2ROW=1 restores the im2row tensor):
+//   S2D[pl][n][sy][sxp][c*4 + py*2 + px] = image[n][c][2*sy + py][2*(sxp - 2) + px]   (12 of 16 channels; 0 in the padding)
+// with rows of SW + 3 pixels (2 zero pixels on the left, 1 on the right) of 16 fp16 channels = 32 B.  The horizontal im2col
+// of the 4x4 conv - the K vector of output pixel x is the 4 consecutive pixels x .. x+3 of that padded row, 128 B - is NOT
+// materialised: the conv's source tensor map has a 32-byte stride in its pixel dimension under a 128-byte row extent
+// (overlapping rows; cuTensorMapEncodeTiled accepts it and the TMA unit delivers exactly these bytes, probed in
+// tools/experiments/tma_overlap_probe.cu), so a [128 pixels][64] box load expands 4.1 KB of global memory into the 16 KB
+// swizzled A tile on the fly.  HBM traffic of the stem's first two kernels: 637 + 1047 MB -> 236 + 632 MB.
+template <int NPLANE>
+__global__ void __launch_bounds__(256)
+stem_s2d_kernel(const float* __restrict__ image, __half* __restrict__ S, int N, int H, int W, long long plane_elems) {
+  const int SH = H / 2, SW = W / 2, PW = SW + 3;
+  const long long total = (long long)N * SH * PW;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int sxp = (int)(t % PW);
+  const int sy = (int)((t / PW) % SH);
+  const int n = (int)(t / ((long long)PW * SH));
+  const int sx = sxp - 2;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+  if (sx >= 0 && sx < SW) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(image + (((size_t)n * 3 + c) * H + (2 * sy + py)) * W + 2 * sx));
+        v[c * 4 + py * 2 + 0] = f.x;
+        v[c * 4 + py * 2 + 1] = f.y;
+      }
+  }
+#pragma unroll
+  for (int pl = 0; pl < NPLANE; ++pl) {
+    uint4 u[2];
+    __half2* hh = reinterpret_cast<__half2*>(u);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float a = v[2 * q], b = v[2 * q + 1];
+      const __half2 h2 = __floats2half2_rn(a, b);
+      if (pl == 0) {
+        hh[q] = h2;
+      } else {
+        const float2 back = __half22float2(h2);
+        hh[q] = __floats2half2_rn(a - back.x, b - back.y);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(S + (size_t)pl * plane_elems + (size_t)t * 16);
+    dst[0] = u[0];
+    dst[1] = u[1];
+  }
+}
+
 // 3x3 stride-2 pad-1 max-pool over NHWC fp16 planes (value = hi + lo).  One thread = one output pixel x 8 channels.
 template <int NPLANE>
 __global__ void __launch_bounds__(256)
@@ -1072,7 +1125,8 @@ struct OpInfo {
   std::vector<__half> w_packed;       // [plane][tap][cout_pad][cin]
   std::vector<float> bias_packed;     // [cout_pad]   (stem: [64]);
   std::vector<float> w_f32;           // kinds 2 / 4 (depthwise 3x3, 3x3/2 image stem): [tap][C] fp32
-  size_t stem_t_offset, stem_s_offset;   // stem scratch: im2row tensor T and the un-pooled conv output S
+  size_t stem_t_offset, stem_s_offset;   // stem scratch: im2row tensor T (or the space-to-depth image) and the un-pooled conv output S
+  int stem_s2d;                          // stem: 1 = space-to-depth image + overlapping-stride tensor map, 0 = materialised im2row tensor
   CUtensorMap src_map, w_map, dst_map;
 };
 
@@ -1402,7 +1456,9 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   op.stage_depth = 1;
   plan_rows_mode(op, planes, 64, 1, true, e->precision);
   if (!op.rows) op.cluster = choose_cluster(op.n_tile, e->batch * op.tiles_w * op.tiles_h, 4);
-  // W2[co][dyi][dxi*12 + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
+  static const bool im2row_env = [] { const char* v = getenv("CNL_STEM_IM2ROW"); return v && atoi(v) != 0; }();
+  op.stem_s2d = im2row_env ? 0 : 1;
+  // W2[co][dyi][dxi*12 (16 in the space-to-depth form) + c*4 + py*2 + px] = w[co][c][ky][kx] with ky <-> (dyi, py), kx <-> (dxi, px):
   //   k - 3 = 2*(d - 2) + p  =>  k = 2*d + p - 1  (k = -1, i.e. d = 0 and p = 0, does not exist -> weight 0)
   std::vector<float> w2((size_t)64 * 4 * 64, 0.f);
   for (int co = 0; co < 64; ++co)
@@ -1415,7 +1471,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
             for (int px = 0; px < 2; ++px) {
               const int kx = 2 * dxi + px - 1;
               if (kx < 0 || kx > 6) continue;
-              w2[((size_t)co * 4 + dyi) * 64 + dxi * 12 + c * 4 + py * 2 + px] = d.weight_host[(((size_t)co * 3 + c) * 7 + ky) * 7 + kx];
+              w2[((size_t)co * 4 + dyi) * 64 + dxi * (op.stem_s2d ? 16 : 12) + c * 4 + py * 2 + px] = d.weight_host[(((size_t)co * 3 + c) * 7 + ky) * 7 + kx];
             }
         }
   pack_split_weights(op, w2, 64, 64, 4, planes);
@@ -1467,7 +1523,8 @@ int cnl_engine_create(cnl_engine** out, const cnl_buffer_desc* buffers, int n_bu
       const size_t half_res = (size_t)batch * (height / 2) * (width / 2) * 64 * 2 * e->planes;
       op.w_offset = off; off += align_up(op.w_packed.size() * 2, 1024);
       op.bias_offset = off; off += align_up(64 * 4, 1024);
-      op.stem_t_offset = off; off += align_up(half_res, 1024);
+      const size_t s2d_bytes = (size_t)batch * (height / 2) * (width / 2 + 3) * 16 * 2 * e->planes;
+      op.stem_t_offset = off; off += align_up(op.stem_s2d ? s2d_bytes : half_res, 1024);
       op.stem_s_offset = off; off += align_up(half_res, 1024);
       op.scratch_offset = 0;
     } else if (op.d.kind >= 2) {
@@ -1531,7 +1588,15 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       cuuint32_t es[4] = {1, 1, 1, 1};
       cuuint32_t box_in[4] = {64, (cuuint32_t)(op.rows ? op.box_w : op.tw), (cuuint32_t)op.th, 1};
       cuuint32_t box_out[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
-      int r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str, box_in, es, "stem im2row");
+      int r;
+      if (op.stem_s2d) {
+        // overlapping rows: pixel stride 32 B (16 channels) under a 128-byte row extent (4 pixels) - see stem_s2d_kernel
+        const cuuint64_t pitch = (sw + 3) * 32;
+        cuuint64_t str2[3] = {32, pitch, sh * pitch};
+        r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str2, box_in, es, "stem space-to-depth (overlapping rows)");
+      } else {
+        r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str, box_in, es, "stem im2row");
+      }
       if (r) return r;
       r = encode_map(&op.dst_map, base + op.stem_s_offset, 4, dims, str, box_out, es, "stem out", CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
@@ -1664,8 +1729,15 @@ int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int f
       __half* S = reinterpret_cast<__half*>(base + op.stem_s_offset);
       const long long npix = (long long)e->batch * SH * SW;
       const int b1 = (int)((npix + 255) / 256);
-      if (planes == 2) stem_im2row_kernel<2><<<b1, 256, 0, st>>>(image, T, e->batch, e->height, e->width, half_plane);
-      else             stem_im2row_kernel<1><<<b1, 256, 0, st>>>(image, T, e->batch, e->height, e->width, half_plane);
+      if (op.stem_s2d) {
+        const long long s2d_plane = (long long)e->batch * SH * (SW + 3) * 16;
+        const int b0 = (int)(((long long)e->batch * SH * (SW + 3) + 255) / 256);
+        if (planes == 2) stem_s2d_kernel<2><<<b0, 256, 0, st>>>(image, T, e->batch, e->height, e->width, s2d_plane);
+        else             stem_s2d_kernel<1><<<b0, 256, 0, st>>>(image, T, e->batch, e->height, e->width, s2d_plane);
+      } else {
+        if (planes == 2) stem_im2row_kernel<2><<<b1, 256, 0, st>>>(image, T, e->batch, e->height, e->width, half_plane);
+        else             stem_im2row_kernel<1><<<b1, 256, 0, st>>>(image, T, e->batch, e->height, e->width, half_plane);
+      }
       p.out_h = SH; p.out_w = SW;
       p.kh = 4; p.kw = 1; p.stride = 1; p.pad_h = 2; p.pad_w = 0; p.kblocks = 1;
       p.src_c_off = 0; p.dst_c_off = 0; p.out_mode = 0; p.cout_real = 64; p.out_nchw = nullptr;

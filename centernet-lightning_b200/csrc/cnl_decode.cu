@@ -1075,7 +1075,7 @@ using namespace cnl;
 extern "C" {
 
 const char* cnl_last_error(void) { return error_buffer(); }
-int cnl_version(void) { return 1000; }
+int cnl_version(void) { return 1002; }   // 1.2: cnl_conv_desc kinds 2-4 (depthwise, fuse, 3x3 stem) + trailing fields, relu = 2 (ReLU6)
 int cnl_compiled_sm(void) { return 100; }
 
 size_t cnl_decode_workspace_bytes(int n, int h, int w) {
