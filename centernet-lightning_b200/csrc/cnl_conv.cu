@@ -81,6 +81,16 @@ struct ConvParams {
   // LDC per value).  As __ldg loads from global memory the same values missed L1 on every tile - 226 KB of the SM's 256 KB
   // are shared memory, and the epilogue's own stores / residual loads evict the three bias lines - and 30-35 % of all warp
   // stall samples of the bandwidth-bound ops (head out-convs, FPN laterals) sat on those loads (ncu source view, r2).
+  // Direct epilogue stores (CNL_DIRECT_STORE=1, off by default): NHWC outputs go from registers to global memory as 256-bit
+  // stores instead of smem staging + TMA stores.  Background (r2, CNL_DEBUG_EPI experiments): NOT issuing the epilogue's
+  // stores makes the whole forward 19 % faster (13.8 -> 11.15 ms) - their waits and the proxy fence cost nothing, the
+  // stores themselves do.  Direct stores measured slower still (14.65 ms).
+  int direct_store;
+  int early_release;            // single accumulator stage, Cout tile 256: drain TMEM into registers, release it, THEN convert / store
+  __half* dst;                  // destination buffer (plane 0), its plane stride in elements and its geometry
+  long long dst_plane_elems;
+  int dst_h, dst_w;
+  int debug;                    // CNL_DEBUG_EPI bit mask, timing experiments only (WRONG results): 1 = epilogue skips its stores
   int bias_in_params;           // 0: more than kParamBias channels, read p.bias from global memory instead
   float bias_c[kParamBias];
 };
@@ -251,12 +261,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             // the leader's barrier collects the bytes of BOTH CTAs' loads for this stage
-            if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+            const bool skip_a = (p.debug & 32) && sx != 0;          // timing experiment: what would sharing A across the kw taps buy?
+            if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (stage_bytes - (skip_a ? NPLANE * kATileBytes : 0)));
             const uint32_t bar = ptx::mapa_u32(&full_bar[stage], 0);
             uint8_t* st = stages + (size_t)stage * stage_bytes;
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl)
-              ptx::tma_load_4d_pair(st + pl * kATileBytes, &src_map, bar, p.src_c_off + kb * kBlockK, cw, ch, img + pl * p.n_img);
+              if (!skip_a) ptx::tma_load_4d_pair(st + pl * kATileBytes, &src_map, bar, p.src_c_off + kb * kBlockK, cw, ch, img + pl * p.n_img);
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl)
               ptx::tma_load_3d_pair(st + NPLANE * kATileBytes + pl * b_half_bytes, &w_map, bar, kb * kBlockK,
@@ -335,16 +346,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         if (fresh) first_slot = ld_slot;
         else if (++first_slot == p.a_slots) first_slot = 0;
-        for (int q = 0; q < n_new; ++q) {
-          ptx::mbar_wait(&a_full_bar[ld_slot], ld_par);
-          if (++ld_slot == p.a_slots) { ld_slot = 0; ld_par ^= 1; }
-        }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
         const uint32_t d_corr = d_tmem + p.corr_off;
         uint32_t first_mma = 0;                               // 0 only for the first MMA of the tile (overwrite the accumulator)
         int slot = first_slot;
         for (int r = 0; r < p.kh; ++r) {
+          // The new input rows are the LAST n_new rows of the window.  Each is waited for only when its taps come up: in
+          // steady state (one new row per output row) that is after the (kh-1)*kw taps that still read the old rows, which
+          // doubles the time the row's TMA load has to land (the slot it refills is released after the r = 0 taps of the
+          // PREVIOUS output row).  Waiting for it at the top of the tile stalled every output row of the stem and layer1.
+          if (r >= p.kh - n_new) {
+            ptx::mbar_wait(&a_full_bar[ld_slot], ld_par);
+            if (++ld_slot == p.a_slots) { ld_slot = 0; ld_par ^= 1; }
+            ptx::tc_fence_after();
+          }
           const uint32_t a_row = ring_addr + (uint32_t)slot * slot_stride;
           for (int sx = 0; sx < p.kw; ++sx) {
             ptx::mbar_wait(&full_bar[stage], phase);           // (resident weights: phase stays 0, the wait falls through)
@@ -509,7 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         // residual (ResNet identity / FPN top-down map): its global loads are issued one 32-channel chunk ahead - the
         // first chunk even before the accumulator is ready - so their latency hides behind the MMAs and the TMEM reads
         const __half* res_px = nullptr;
-        if (p.res != nullptr && valid)
+        if (!PAIR && p.res != nullptr && valid)          // (residual ops never run as CTA pairs: see prepare_conv)
           res_px = p.res + (((long long)img * p.res_h + (h / p.res_up)) * p.res_w + (w / p.res_up)) * p.res_c;
         uint4 res_a[NPLANE * 4], res_b[NPLANE * 4];
         auto prefetch_res = [&](int c32, uint4 (&dst)[NPLANE * 4]) {
@@ -537,9 +553,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         ptx::tc_fence_after();
 
         const int hq = h0 + lb_dh, wq = w0 + lb_dw;           // first pixel of this warp's 32 (store box origin)
-        auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4]) {
+        // the accumulator values of one 32-channel chunk of this thread's pixel (main + correction accumulator)
+        auto drain = [&](int c32, float (&v)[32]) {
           uint32_t r[32];
-          float v[32];
           ptx::tmem_ld_32x32b_x32(taddr + c32 * 32, r);
           if (CORR) {
             uint32_t rc[32];
@@ -552,6 +568,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
+        };
+        auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4], float (&v)[32]) {
           const int cb = n_idx * p.n_tile + c32 * 32;
 #pragma unroll
           if (p.bias_in_params) {
@@ -594,10 +612,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
           // finish reading its staging buffer; with ONE buffer per warp every chunk waited for the previous chunk's store
           // (80 % of the epilogue's busy samples, and the epilogue is exposed whenever the accumulator is not double
           // buffered).  With a ring of `stage_depth` buffers only the store issued depth chunks ago has to be done.
+          if (p.debug & 1) return;
+          if (p.direct_store) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float a = v[2 * t], b = v[2 * t + 1];
+              const __half2 h2 = __floats2half2_rn(a, b);
+              hi[t] = *reinterpret_cast<const uint32_t*>(&h2);
+              if (NPLANE == 2) {
+                const float2 back = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
+                lo[t] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+            }
+            if (valid) {
+              // dst_up == 2: the destination has twice the resolution; phase -1 fills the 2x2 block (conv + nearest x2), a
+              // phase 0..3 writes one sub-pixel (one phase of a stride-2 transposed conv)
+              const int up = p.dst_up == 2 ? 2 : 1;
+              for (int ph = 0; ph < up * up; ++ph) {
+                if (up == 2 && p.dst_phase >= 0 && ph != p.dst_phase) continue;
+                const int oh = h * up + (ph >> 1), ow = w * up + (ph & 1);
+                __half* dp = p.dst + (((long long)img * p.dst_h + oh) * p.dst_w + ow) * p.dst_c + p.dst_c_off + cb;
+                ptx::st_global_256(dp, reinterpret_cast<const uint32_t(&)[8]>(hi[0]));
+                ptx::st_global_256(dp + 16, reinterpret_cast<const uint32_t(&)[8]>(hi[8]));
+                if (NPLANE == 2) {
+                  ptx::st_global_256(dp + p.dst_plane_elems, reinterpret_cast<const uint32_t(&)[8]>(lo[0]));
+                  ptx::st_global_256(dp + p.dst_plane_elems + 16, reinterpret_cast<const uint32_t(&)[8]>(lo[8]));
+                }
+              }
+            }
+            return;
+          }
           uint8_t* my_stage = my_stage_base + (size_t)sbuf * NPLANE * kStageWarpBytes;
           if (++sbuf == p.stage_depth) sbuf = 0;
           if (lane == 0) {
-            if (p.stage_depth >= 3)      ptx::tma_store_wait_read<2>();
+            if (p.debug & 4) {}
+            else if (p.stage_depth >= 3) ptx::tma_store_wait_read<2>();
             else if (p.stage_depth == 2) ptx::tma_store_wait_read<1>();
             else                         ptx::tma_store_wait_read<0>();
           }
@@ -621,9 +672,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             *reinterpret_cast<uint4*>(my_stage + off) = hi;
             if (NPLANE == 2) *reinterpret_cast<uint4*>(my_stage + kStageWarpBytes + off) = lo;
           }
-          ptx::fence_proxy_async_smem();
+          if (!(p.debug & 2)) ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.debug & 8)) {
             if (p.dst_up == 2) {
               // destination at twice the resolution, viewed as [n][y][py][x][px*C + c]: one store per sub-pixel.
               // All four = conv followed by a nearest x2 upsample; a single one = one phase of a stride-2 transposed conv.
@@ -635,19 +686,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                                     hq, img + pl * p.n_img);
               }
             } else {
-#pragma unroll
-              for (int pl = 0; pl < NPLANE; ++pl)
-                ptx::tma_store_4d(&dst_map, my_stage + pl * kStageWarpBytes, p.dst_c_off + cb, wq, hq, img + pl * p.n_img);
+              ptx::tma_store_5d(&dst_map, my_stage, p.dst_c_off + cb, wq, hq, (p.debug & 64) ? (1 << 20) : img, 0);        // both planes in one request (debug 64: fully out of bounds = clipped, timing experiment)
             }
             ptx::tma_store_commit();
           }
         };
+        if constexpr (PAIR) {
+          if (p.early_release) {
+            // Single accumulator stage (main + correction accumulators of a 256-wide tile fill the 512 TMEM columns): the
+            // MMA warp cannot start the next tile before this epilogue has released the accumulator, and the store path
+            // (convert, stage, wait for the previous chunk's TMA store, store) is most of the epilogue.  So the warp first
+            // drains its 4 x 32 columns into registers - the main accumulator straight into its final registers, the
+            // correction accumulator in 16-column pieces, 128 + 16 live values under the 168-register cap of a 10-warp CTA -
+            // hands the accumulator back, and only then converts and stores, overlapped with the next tile's MMAs.
+            float acc[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32b_x32_f(taddr + (c_lo + c) * 32, acc[c]);
+            ptx::tmem_ld_wait();
+            if (CORR) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  uint32_t rc[16];
+                  ptx::tmem_ld_32x32b_x16(taddr + p.corr_off + (c_lo + c) * 32 + hf * 16, rc);
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) acc[c][hf * 16 + j] += __uint_as_float(rc[j]);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (crank != 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(&tmem_empty_bar[as], 0));
+              else            ptx::mbar_arrive(&tmem_empty_bar[as]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) chunk(c_lo + c, res_a, acc[c]);
+            continue;                                     // (the accumulator was released above)
+          }
+        }
         for (int c32 = c_lo; c32 < c_hi; c32 += 2) {
+          float v[32];
           if (c32 + 1 < c_hi) prefetch_res(c32 + 1, res_b);
-          chunk(c32, res_a);
+          drain(c32, v);
+          chunk(c32, res_a, v);
           if (c32 + 1 < c_hi) {
             if (c32 + 2 < c_hi) prefetch_res(c32 + 2, res_a);
-            chunk(c32 + 1, res_b);
+            drain(c32 + 1, v);
+            chunk(c32 + 1, res_b, v);
           }
         }
       } else {
@@ -1170,6 +1257,13 @@ static int encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* di
 
 static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+// CNL_DIRECT_STORE=1: epilogue writes 256-bit global stores from registers instead of smem staging + TMA stores (measured
+// SLOWER: forward 13.8 -> 14.65 ms; kept for A/B timing)
+static bool direct_store_enabled() {
+  static const bool on = [] { const char* v = getenv("CNL_DIRECT_STORE"); return v && atoi(v) != 0; }();
+  return on;
+}
+
 // CTAs per cluster that share one multicast weight tile.  Opt-in through CNL_CLUSTER=2 (or 4): measured on B200 the
 // kernel is tensor/power-bound, not L2-bound, so halving the weight traffic changes nothing (1.229 vs 1.220 ms on the
 // 256->256 tower conv; cluster 4 strands SMs and is slower); default 1.  Each CTA loads
@@ -1263,7 +1357,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   op.store_h = 32 / op.store_w;
   const int planes = e->planes;
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
-  const int staging = dst.fp32_nchw ? 0 : kEpiWarps * planes * kStageWarpBytes;
+  const int staging = (dst.fp32_nchw || direct_store_enabled()) ? 0 : kEpiWarps * planes * kStageWarpBytes;
   op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - staging) / stage_bytes);
   if (op.num_stages < 2) return fail(CNL_ERR_UNSUPPORTED, "conv tile does not fit shared memory");
   op.cluster = 1;                                    // decided below, after the row-rolling and CTA-pair forms
@@ -1288,7 +1382,7 @@ static int prepare_conv(cnl_engine* e, OpInfo& op) {
   // Cout tiles of 128 as pairs (CNL_PAIR128=1) measure 4 % SLOWER than the single-CTA [hi|lo] form: there the A operand's
   // shared-memory read (streamed twice instead of three times) matters more than the fill traffic
   static const bool pair128 = [] { const char* v = getenv("CNL_PAIR128"); return v && atoi(v) != 0; }();
-  if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && (op.n_tile == 256 || (op.n_tile == 128 && pair128)) && !op.rows && !dst.fp32_nchw &&
+  if (pair_on && e->precision == CNL_PRECISION_SPLIT && op.corr && (op.n_tile == 256 || (op.n_tile == 128 && pair128)) && !op.rows && !dst.fp32_nchw && d.residual < 0 &&
       cluster_env() <= 1 && e->batch * op.tiles_w * op.tiles_h >= 2 &&
       e->batch * op.tiles_w * op.tiles_h * op.n_tiles >= pair_min_tiles) {     // short launches (layer3/4) measure 5-7 % slower as pairs
     op.pair = 1;
@@ -1345,7 +1439,7 @@ static bool plan_rows_mode(OpInfo& op, int planes, int cin, int stride, bool nhw
   if (box_w > 256) return false;
   const int slot_bytes = (box_w * kBlockK * 2 + 1023) / 1024 * 1024;
   const int b_stage = planes * op.n_tile * kBlockK * 2;
-  const int staging = kEpiWarps * planes * kStageWarpBytes;
+  const int staging = direct_store_enabled() ? 0 : kEpiWarps * planes * kStageWarpBytes;
   // Row slots: the oldest row's slot is released after the r = 0 taps (see the MMA warp), so kh slots already give the
   // producer two thirds of an output row of look-ahead; every further slot costs weight stages, and it is the number of
   // weight tiles in flight that hides their L2 latency.  Take the largest ring that still leaves kMinRowsStages stages
@@ -1447,7 +1541,7 @@ static int prepare_stem(cnl_engine* e, OpInfo& op) {
   op.store_h = 32 / op.store_w;
   const int planes = e->planes;
   const int stage_bytes = planes * (kATileBytes + op.n_tile * kBlockK * 2);
-  op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - kEpiWarps * planes * kStageWarpBytes) / stage_bytes);
+  op.num_stages = std::min(kMaxStages, (kSmemLimit - 1024 - (direct_store_enabled() ? 0 : kEpiWarps * planes * kStageWarpBytes)) / stage_bytes);
   op.cluster = 1;
   op.cat = (e->precision == CNL_PRECISION_SPLIT) && cat_enabled();
   op.corr = op.cat;                        // K = 256: the correction accumulator only comes with the cat MMA
@@ -1598,7 +1692,13 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
         r = encode_map(&op.src_map, base + op.stem_t_offset, 4, dims, str, box_in, es, "stem im2row");
       }
       if (r) return r;
-      r = encode_map(&op.dst_map, base + op.stem_s_offset, 4, dims, str, box_out, es, "stem out", CU_TENSOR_MAP_SWIZZLE_64B);
+      {
+        cuuint64_t od[5] = {64, sw, sh, (cuuint64_t)e->batch, (cuuint64_t)planes};
+        cuuint64_t os[4] = {128, sw * 128, sh * sw * 128, (cuuint64_t)e->batch * sh * sw * 128};
+        cuuint32_t ob[5] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1, (cuuint32_t)planes};
+        cuuint32_t oe[5] = {1, 1, 1, 1, 1};
+        r = encode_map(&op.dst_map, base + op.stem_s_offset, 5, od, os, ob, oe, "stem out", CU_TENSOR_MAP_SWIZZLE_64B);
+      }
       if (r) return r;
       cuuint64_t wd[3] = {64, 64, (cuuint64_t)4 * planes};
       cuuint64_t ws[2] = {128, 64 * 128};
@@ -1644,11 +1744,14 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       int r = encode_map(&op.dst_map, base + dst.offset, 5, dims, str, box, es, "dst (x2)", CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
     } else if (!dst.fp32_nchw) {
-      cuuint64_t dims[4] = {(cuuint64_t)dst.channels, (cuuint64_t)dst.w, (cuuint64_t)dst.h, (cuuint64_t)e->batch * planes};
-      cuuint64_t str[3] = {(cuuint64_t)dst.channels * 2, (cuuint64_t)dst.w * dst.channels * 2, (cuuint64_t)dst.h * dst.w * dst.channels * 2};
-      cuuint32_t box[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};      // 32 channels = 64-byte rows
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      int r = encode_map(&op.dst_map, base + dst.offset, 4, dims, str, box, es, "dst", CU_TENSOR_MAP_SWIZZLE_64B);
+      // [plane][n][h][w][c] with the plane as its own (5th) dimension: ONE store request writes a warp's chunk to both planes
+      // (the staging buffers of the two planes are adjacent) - the TMA unit's cost is per request, not per byte
+      cuuint64_t dims[5] = {(cuuint64_t)dst.channels, (cuuint64_t)dst.w, (cuuint64_t)dst.h, (cuuint64_t)e->batch, (cuuint64_t)planes};
+      cuuint64_t str[4] = {(cuuint64_t)dst.channels * 2, (cuuint64_t)dst.w * dst.channels * 2, (cuuint64_t)dst.h * dst.w * dst.channels * 2,
+                           (cuuint64_t)dst.plane_elems * 2};
+      cuuint32_t box[5] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1, (cuuint32_t)planes};      // 32 channels = 64-byte rows
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      int r = encode_map(&op.dst_map, base + dst.offset, 5, dims, str, box, es, "dst", CU_TENSOR_MAP_SWIZZLE_64B);
       if (r) return r;
     } else {
       op.dst_map = op.src_map;
@@ -1713,12 +1816,19 @@ int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int f
     p.sigmoid = (sigmoid_buffer >= 0 && d.dst == sigmoid_buffer) ? 1 : 0;
     p.wscale_inv = 1.0f / op.wscale;
     p.bias = reinterpret_cast<const float*>(base + op.bias_offset);
+    static const int dbg_env = [] { const char* v = getenv("CNL_DEBUG_EPI"); return v ? atoi(v) : 0; }();
+    p.debug = dbg_env;
     p.bias_in_params = (d.kind <= 1 && op.bias_packed.size() <= (size_t)kParamBias) ? 1 : 0;
     if (p.bias_in_params) std::memcpy(p.bias_c, op.bias_packed.data(), op.bias_packed.size() * sizeof(float));
     p.res = nullptr; p.res_up = 1; p.res_c = 0; p.res_h = 0; p.res_w = 0; p.res_plane_elems = 0;
     p.num_stages = op.num_stages; p.store_w = op.store_w; p.store_h = op.store_h; p.cluster = op.cluster;
     p.acc_stages = op.acc_stages; p.corr_off = op.corr_off; p.cat = op.cat;
     p.dst_up = 1; p.dst_phase = -1; p.dst_c = dst.channels;
+    p.direct_store = direct_store_enabled() ? 1 : 0;
+    static const bool early_on = [] { const char* v = getenv("CNL_EARLY_RELEASE"); return !(v && atoi(v) == 0); }();
+    p.early_release = (early_on && d.kind == 0 && op.pair && op.acc_stages == 1 && op.n_tile == 256 && !dst.fp32_nchw) ? 1 : 0;
+    p.dst = dst.fp32_nchw ? nullptr : reinterpret_cast<__half*>(base + dst.offset);
+    p.dst_plane_elems = dst.plane_elems; p.dst_h = dst.h; p.dst_w = dst.w;
     p.a_slots = op.a_slots; p.a_slot_bytes = op.a_slot_bytes; p.box_w = op.box_w; p.stage_depth = op.stage_depth;
     p.w_resident = op.rows ? op.w_resident : 0;
     if (d.kind == 1) {
@@ -1741,6 +1851,7 @@ int cnl_engine_forward_act(cnl_engine* e, void* arena, const float* image, int f
       p.out_h = SH; p.out_w = SW;
       p.kh = 4; p.kw = 1; p.stride = 1; p.pad_h = 2; p.pad_w = 0; p.kblocks = 1;
       p.src_c_off = 0; p.dst_c_off = 0; p.out_mode = 0; p.cout_real = 64; p.out_nchw = nullptr;
+      p.dst = S; p.dst_plane_elems = half_plane; p.dst_h = SH; p.dst_w = SW; p.dst_c = 64;      // the un-pooled conv output
       CNL_CUDA_CHECK(launch_conv(p, op));
       const long long total = (long long)e->batch * (SH / 2) * (SW / 2) * 8;
       const int b2 = (int)((total + 255) / 256);
