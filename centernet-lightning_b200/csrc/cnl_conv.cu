@@ -686,7 +686,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
                                     hq, img + pl * p.n_img);
               }
             } else {
-              ptx::tma_store_5d(&dst_map, my_stage, p.dst_c_off + cb, wq, hq, (p.debug & 64) ? (1 << 20) : img, 0);        // both planes in one request (debug 64: fully out of bounds = clipped, timing experiment)
+              ptx::tma_store_5d(&dst_map, my_stage, p.dst_c_off + cb, wq, hq, (p.debug & 64) ? (1 << 20) : ((p.debug & 128) ? (img & 1) : img), 0);        // both planes in one request (debug 64: fully out of bounds = clipped, timing experiment)
             }
             ptx::tma_store_commit();
           }
