@@ -15,9 +15,9 @@ python tools/bench_decode.py --net > $out/${tag}_decode_bench.log 2>&1
 python tools/bench_tracker_costs.py > $out/${tag}_tracker_costs.log 2>&1
 python tools/bench_inference.py > $out/${tag}_inference_folder.json 2> $out/${tag}_inference_folder.err
 # launch list of 2 bench steps (shares, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:cnl:: -s 216 -c 108 --csv --log-file $out/${tag}_bench_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-fast > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:conv_tc_kernel|stem_|pool_planes|peaks_|select_gather' -s 216 -c 108 --csv --log-file $out/${tag}_bench_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-fast > /dev/null 2>&1
 # per-op metrics of one eager forward + decode (54 launches; the first detect() is skipped)
-ncu --metrics $M --clock-control none -k regex:cnl:: -s 108 -c 54 --csv --log-file $out/${tag}_forward_per_op_ncu.csv python tools/run_forward_once.py > $out/${tag}_forward_ops.txt 2>&1
+ncu --metrics $M --clock-control none -k 'regex:conv_tc_kernel|stem_|pool_planes|peaks_|select_gather' -s 108 -c 54 --csv --log-file $out/${tag}_forward_per_op_ncu.csv python tools/run_forward_once.py > $out/${tag}_forward_ops.txt 2>&1
 # full captures: dominant conv (CTA-pair form), row-rolling layer1 conv, decode kernels
 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 50 -c 1 -f -o $out/${tag}_tower_conv python tools/run_op.py heads.heatmap.block_2 2 > $out/${tag}_tower_conv.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 50 -c 1 -f -o $out/${tag}_layer1_rows python tools/run_op.py backbone.layer1.1.conv1 2 > $out/${tag}_layer1_rows.log 2>&1
