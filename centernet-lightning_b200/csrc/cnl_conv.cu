@@ -267,7 +267,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             uint8_t* st = stages + (size_t)stage * stage_bytes;
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl)
-              if (!skip_a) ptx::tma_load_4d_pair(st + pl * kATileBytes, &src_map, bar, p.src_c_off + kb * kBlockK, cw, ch, img + pl * p.n_img);
+              if (!skip_a) ptx::tma_load_4d_pair(st + pl * kATileBytes, &src_map, bar, p.src_c_off + kb * kBlockK, cw, ch,
+                                                 (((p.debug & 256) && img < p.n_img) ? (img & 1) : img) + pl * p.n_img);   // debug 256: L2-resident input (timing experiment)
 #pragma unroll
             for (int pl = 0; pl < NPLANE; ++pl)
               ptx::tma_load_3d_pair(st + NPLANE * kATileBytes + pl * b_half_bytes, &w_map, bar, kb * kBlockK,

@@ -1,4 +1,7 @@
-for d in 0 128; do
+# SM clock / board power of the dominant conv (heads.heatmap.block_2, looped 400x) under the CNL_DEBUG_EPI timing experiments:
+#   0 = real stores, 64 = TMA stores issued fully out of bounds (clipped: nothing written), 128 = stores confined to a 2-image
+#   (L2-resident) region, 256 = input reads confined to a 2-image region.  Results of round 2: 1477 MHz / 1792 / 1728 / 1477.
+for d in 0 64 128 256; do
   nvidia-smi --query-gpu=clocks.sm,power.draw --format=csv,noheader -lms 50 > gpurun_out/r3i_clk_$d.csv &
   SMI=$!
   CNL_DEBUG_EPI=$d python tools/op_times.py split 400 heatmap.block_2 > gpurun_out/r3i_ops_$d.log 2>&1
