@@ -572,7 +572,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         };
         auto chunk = [&](int c32, const uint4 (&res)[NPLANE * 4], float (&v)[32]) {
           const int cb = n_idx * p.n_tile + c32 * 32;
-#pragma unroll
           if (p.bias_in_params) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.wscale_inv, p.bias_c[cb + j]);
@@ -1682,7 +1681,6 @@ int cnl_engine_upload(cnl_engine* e, void* arena, void* stream) {
       cuuint64_t str[3] = {128, sw * 128, sh * sw * 128};
       cuuint32_t es[4] = {1, 1, 1, 1};
       cuuint32_t box_in[4] = {64, (cuuint32_t)(op.rows ? op.box_w : op.tw), (cuuint32_t)op.th, 1};
-      cuuint32_t box_out[4] = {32, (cuuint32_t)op.store_w, (cuuint32_t)op.store_h, 1};
       int r;
       if (op.stem_s2d) {
         // overlapping rows: pixel stride 32 B (16 channels) under a 128-byte row extent (4 pixels) - see stem_s2d_kernel
